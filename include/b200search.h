@@ -1,0 +1,154 @@
+/*
+ * b200search.h -- C ABI of libb200search.so (sm_100a).
+ *
+ * Drop-in boundary for ONE hot path of Axionis47/semantic-search-kd: exact
+ * inner-product / cosine top-k of 384-d embeddings against a corpus matrix.
+ * The reference has no FFI of its own for this path: it is a duck-typed Python
+ * class (FAISSIndexBuilder, source absent from the tree) that forwards to
+ * faiss-cpu.  Each entry point below names the reference call it replaces
+ * (paths relative to /root/reference).  All functions are extern "C", take
+ * plain pointers and sizes, never throw, never abort; they return B2S_OK (0)
+ * or a negative B2S_ERR_* code with a thread-local message in b2s_last_error().
+ *
+ * Threading: one in-flight call per index handle (calls on the same handle are
+ * serialised by an internal mutex), matching the reference's single-worker,
+ * event-loop-thread use of .search (src/serve/app.py:258,293; src/config.py:213).
+ */
+#ifndef B200SEARCH_H
+#define B200SEARCH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B2S_API __attribute__((visibility("default")))
+#else
+#define B2S_API
+#endif
+
+typedef struct b2s_index b2s_index;
+
+enum {
+    B2S_OK = 0,
+    B2S_ERR_INVALID = -1,     /* bad argument (NULL, dim mismatch, k < 0 ...)        */
+    B2S_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed                  */
+    B2S_ERR_NOMEM = -3,       /* device or host allocation failed                     */
+    B2S_ERR_UNSUPPORTED = -4, /* shape outside what the kernels are built for         */
+    B2S_ERR_NO_DEVICE = -5    /* no sm_100 device / CUDA driver not present           */
+};
+
+enum { B2S_METRIC_INNER_PRODUCT = 0, B2S_METRIC_COSINE = 1 };
+enum { B2S_DTYPE_F32 = 0, B2S_DTYPE_BF16 = 1 };
+enum { B2S_PATH_AUTO = 0, B2S_PATH_SCAN = 1, B2S_PATH_TENSOR = 2 };
+
+/* Per-call counters of the last search on a handle (b2s_last_stats). */
+typedef struct b2s_stats {
+    int32_t path;            /* B2S_PATH_SCAN or B2S_PATH_TENSOR actually taken                 */
+    int32_t kernel_launches; /* kernels of this library launched by the last search call        */
+    int32_t seeded;          /* 1 if a threshold-seeding pre-pass ran                            */
+    int32_t reserved;
+    int64_t corpus_bytes;    /* algorithmic bytes of one pass over the local shard              */
+    int64_t passes;          /* how many times the dominant kernel streamed the shard           */
+    float dominant_ms;       /* device time of the dominant kernel(s), only if timing enabled    */
+    float total_ms;          /* device time of the whole call, only if timing enabled            */
+} b2s_stats;
+
+/* Library / build identification. */
+B2S_API int b2s_version(void);
+B2S_API const char* b2s_last_error(void);
+B2S_API int b2s_device_count(void);
+
+/*
+ * Replaces FAISSIndexBuilder(embedding_dim, index_type, metric)
+ *   scripts/build_faiss_index.py:49-53, src/serve/app.py:427-429, and
+ *   faiss.IndexFlatIP(384) (tests/conftest.py:184).
+ * metric COSINE L2-normalises rows at add time and queries at search time and
+ * then uses the inner product (configs/index.yaml:11,30).
+ */
+B2S_API int b2s_create(int dim, int metric, int device, b2s_index** out);
+B2S_API int b2s_destroy(b2s_index* idx);
+
+/* Pre-size the device corpus buffer for n_rows rows (optional). */
+B2S_API int b2s_reserve(b2s_index* idx, int64_t n_rows);
+
+/*
+ * Replaces index.add(x) (tests/conftest.py:185) and the add loop inside
+ * FAISSIndexBuilder.build_from_parquet (scripts/build_faiss_index.py:55-62).
+ * rows: row-major [n, dim]; is_device != 0 means a device pointer on the
+ * index's device.  Rows are stored as bf16 (round-to-nearest-even).
+ */
+B2S_API int b2s_add_f32(b2s_index* idx, const float* rows, int64_t n, int is_device);
+B2S_API int b2s_add_bf16(b2s_index* idx, const void* rows, int64_t n, int is_device);
+
+/* index.ntotal (scripts/build_faiss_index.py:72). */
+B2S_API int64_t b2s_ntotal(const b2s_index* idx);
+B2S_API int b2s_dim(const b2s_index* idx);
+B2S_API int b2s_reset(b2s_index* idx); /* drop all rows, keep the allocation */
+
+/* Global id of local row 0 (row-sharded corpus: SURVEY.md 8e). */
+B2S_API int b2s_set_id_offset(b2s_index* idx, int64_t offset);
+
+/*
+ * Tuning / behaviour switches, by name:
+ *   "path"        B2S_PATH_*           force a kernel family (default AUTO)
+ *   "seed"        -1 auto | 0 off | 1 on   threshold-seeding pre-pass
+ *   "scan_ctas_per_sm"  CTAs per SM of the scan kernel (default 2)
+ *   "keep_f32"    1: keep an fp32 copy of added rows for exact re-scoring
+ *   "rescore_pad" extra candidates re-scored in fp32 when keep_f32 is on
+ *   "timing"      1: record CUDA-event timings into b2s_stats (adds syncs)
+ */
+B2S_API int b2s_set_option(b2s_index* idx, const char* name, int64_t value);
+B2S_API int64_t b2s_get_option(const b2s_index* idx, const char* name);
+
+/*
+ * Replaces FAISSIndexBuilder.search(query_emb, k) -> (distances, indices)
+ *   call site src/serve/app.py:293-295, consumer :299-317; faiss Index.search.
+ * HOST buffers: queries fp32 row-major [nq, dim]; out_scores [nq, k] float32
+ * descending; out_ids [nq, k] int64; unfilled slots (-FLT_MAX, -1).
+ * Host<->device copies happen inside the call.
+ */
+B2S_API int b2s_search(b2s_index* idx, const float* queries, int64_t nq, int k, float* out_scores,
+                       int64_t* out_ids);
+
+/*
+ * Same search with DEVICE buffers on the index's device, enqueued on
+ * cuda_stream (a cudaStream_t; NULL = the legacy default stream).  q_dtype is
+ * B2S_DTYPE_F32 or B2S_DTYPE_BF16.  Returns after enqueueing; no host sync.
+ * For a row-sharded corpus this is the per-shard "local top-k" whose outputs
+ * feed the all-gather and b2s_merge_device.
+ */
+B2S_API int b2s_search_device(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, int k,
+                              float* out_scores, int64_t* out_ids, void* cuda_stream);
+
+/*
+ * Merge G sorted candidate lists per query into the global top-k (after the
+ * NCCL all-gather of a row-sharded search).  scores/ids: device, [G, nq, k];
+ * lists must be ordered by ascending id range (rank order) so that ties keep
+ * the lower id.  Outputs device [nq, k].
+ */
+B2S_API int b2s_merge_device(int device, const float* scores, const int64_t* ids, int g, int64_t nq,
+                             int k, float* out_scores, int64_t* out_ids, void* cuda_stream);
+
+/*
+ * Replaces StudentModel.compute_similarity(q, d) -> [nq, nd]
+ *   tests/test_student_model.py:104-124; src/mining/miners.py:228-233;
+ *   src/kd/eval.py:75.  HOST fp32 buffers, out [nq, nd] row-major.
+ */
+B2S_API int b2s_similarity(int device, const float* q, int64_t nq, const float* d, int64_t nd,
+                           int dim, float* out);
+
+/* Read rows [start, start+n) back as fp32 into a host buffer (save()). */
+B2S_API int b2s_read_rows_f32(b2s_index* idx, int64_t start, int64_t n, float* out_host);
+
+/* Device pointer of the bf16 corpus [ntotal, dim] (borrowed; valid until the next add). */
+B2S_API const void* b2s_rows_device(const b2s_index* idx);
+
+B2S_API int b2s_last_stats(const b2s_index* idx, b2s_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SEARCH_H */

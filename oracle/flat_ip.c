@@ -1,0 +1,346 @@
+/*
+ * oracle/flat_ip.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement ("port") of the exact inner-product top-k search the
+ * reference performs through faiss.IndexFlatIP / numpy:
+ *   - identity of the path:   /root/reference/tests/conftest.py:184-185
+ *       faiss.IndexFlatIP(384); index.add(fp32 unit-norm rows)
+ *   - numpy restatements in the reference itself:
+ *       src/kd/eval.py:75,86            scores = q @ c.T ; argsort[::-1][:k]
+ *       scripts/simple_eval.py:25,35    np.matmul(Q, C.T) ; argsort[::-1][:k]
+ *       scripts/evaluate_production.py:94,98
+ *   - output convention:      src/serve/app.py:299-301  ([nq,k], id -1 = none)
+ *   - ANCE margin filter:     src/mining/miners.py:237-247
+ *
+ * PARITY UNPINNED: the arithmetic of the reference lives in the third-party
+ * dependency faiss-cpu ^1.7.4 (pyproject.toml:15), which is neither vendored
+ * under /root/reference nor installable here, and no reference test pins a
+ * retrieved id or score.  This file restates faiss' published IndexFlatIP
+ * semantics: score = sum_i q_i * x_i, the k largest scores per query returned
+ * in descending order, int64 labels, unfilled slots = (-FLT_MAX, -1), a later
+ * row never displaces an earlier row of equal score (strict '>' replacement).
+ * Ties in the OUTPUT are ordered by ascending id (deterministic refinement).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may load this library.  The product path never does.
+ *
+ * Build: see oracle/Makefile (gcc -O3 -mavx2 -mfma -fopenmp -shared).
+ */
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------ */
+/* dot products                                                        */
+/* ------------------------------------------------------------------ */
+
+/* fp32 products, fp32 accumulate in 8 partial sums (the shape of faiss'
+ * AVX2 fvec_inner_product), then a pairwise horizontal add. */
+static inline float dot_f32(const float* a, const float* b, int d) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int i = 0;
+    for (; i + 8 <= d; i += 8)
+        for (int j = 0; j < 8; ++j) acc[j] += a[i + j] * b[i + j];
+    float tail = 0.f;
+    for (; i < d; ++i) tail += a[i] * b[i];
+    float s0 = (acc[0] + acc[4]) + (acc[2] + acc[6]);
+    float s1 = (acc[1] + acc[5]) + (acc[3] + acc[7]);
+    return (s0 + s1) + tail;
+}
+
+/* fp32 inputs, exact products and accumulation in fp64, rounded once.
+ * This is the adjudicator used by the parity rule. */
+static inline float dot_f64(const float* a, const float* b, int d) {
+    double acc[4] = {0, 0, 0, 0};
+    int i = 0;
+    for (; i + 4 <= d; i += 4)
+        for (int j = 0; j < 4; ++j) acc[j] += (double)a[i + j] * (double)b[i + j];
+    for (; i < d; ++i) acc[0] += (double)a[i] * (double)b[i];
+    return (float)((acc[0] + acc[2]) + (acc[1] + acc[3]));
+}
+
+/* ------------------------------------------------------------------ */
+/* bounded result set: "better" = higher score, then lower id          */
+/* ------------------------------------------------------------------ */
+
+typedef struct {
+    float s;
+    int64_t id;
+} orc_hit;
+
+static inline int hit_better(float s, int64_t id, float s2, int64_t id2) {
+    return (s > s2) || (s == s2 && id < id2);
+}
+
+/* binary min-heap on "better": root = the worst kept hit */
+typedef struct {
+    orc_hit* h;
+    int k;
+    int n;
+} orc_heap;
+
+static inline void heap_sift_down(orc_heap* hp, int i) {
+    orc_hit* h = hp->h;
+    int n = hp->n;
+    orc_hit v = h[i];
+    for (;;) {
+        int c = 2 * i + 1;
+        if (c >= n) break;
+        if (c + 1 < n && hit_better(h[c].s, h[c].id, h[c + 1].s, h[c + 1].id)) c = c + 1;
+        /* c is now the worse child */
+        if (hit_better(h[c].s, h[c].id, v.s, v.id)) break; /* child better than v: stop */
+        h[i] = h[c];
+        i = c;
+    }
+    h[i] = v;
+}
+
+static inline void heap_sift_up(orc_heap* hp, int i) {
+    orc_hit* h = hp->h;
+    orc_hit v = h[i];
+    while (i > 0) {
+        int p = (i - 1) / 2;
+        if (hit_better(v.s, v.id, h[p].s, h[p].id)) break; /* v better than parent: stop */
+        h[i] = h[p];
+        i = p;
+    }
+    h[i] = v;
+}
+
+static inline void heap_offer(orc_heap* hp, float s, int64_t id) {
+    if (hp->k == 0) return;
+    if (hp->n < hp->k) {
+        hp->h[hp->n].s = s;
+        hp->h[hp->n].id = id;
+        hp->n++;
+        heap_sift_up(hp, hp->n - 1);
+    } else if (hit_better(s, id, hp->h[0].s, hp->h[0].id)) {
+        hp->h[0].s = s;
+        hp->h[0].id = id;
+        heap_sift_down(hp, 0);
+    }
+}
+
+static int hit_cmp_desc(const void* a, const void* b) {
+    const orc_hit* x = (const orc_hit*)a;
+    const orc_hit* y = (const orc_hit*)b;
+    if (hit_better(x->s, x->id, y->s, y->id)) return -1;
+    if (hit_better(y->s, y->id, x->s, x->id)) return 1;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* public entry points                                                 */
+/* ------------------------------------------------------------------ */
+
+/*
+ * Exact top-k of Q (nq x d) against X (n x d), both row-major fp32.
+ *   acc_mode 0: fp32 accumulate (faiss-like), 1: fp64 accumulate.
+ *   id_offset : added to row indices (streaming over corpus blocks).
+ *   merge     : if nonzero, D/I already hold a valid sorted result of a
+ *               previous block (padding = (-FLT_MAX,-1)) that is merged in.
+ * Output: D[nq*k] descending, I[nq*k]; unfilled = (-FLT_MAX, -1).
+ * Returns 0, or -1 on bad arguments / allocation failure.
+ */
+ORC_API int orc_flat_ip_topk(const float* X, int64_t n, int d, const float* Q, int64_t nq, int k,
+                             int acc_mode, int64_t id_offset, int merge, float* D, int64_t* I,
+                             int nthreads) {
+    if (d <= 0 || n < 0 || nq < 0 || k < 0) return -1;
+    if (nq == 0 || k == 0) return 0;
+#ifdef _OPENMP
+    int T = nthreads > 0 ? nthreads : omp_get_max_threads();
+#else
+    int T = 1;
+#endif
+    if (T < 1) T = 1;
+    if ((int64_t)T > n / 1024 + 1) T = (int)(n / 1024 + 1);
+
+    /* per-thread, per-query heaps */
+    const int QB = 16; /* query block kept hot in L1 */
+    orc_hit* store = (orc_hit*)malloc(sizeof(orc_hit) * (size_t)T * (size_t)QB * (size_t)k);
+    if (!store) return -1;
+
+    for (int64_t q0 = 0; q0 < nq; q0 += QB) {
+        int qb = (int)((nq - q0) < QB ? (nq - q0) : QB);
+        int* cnt = (int*)calloc((size_t)T * QB, sizeof(int));
+        if (!cnt) {
+            free(store);
+            return -1;
+        }
+#ifdef _OPENMP
+#pragma omp parallel num_threads(T)
+#endif
+        {
+#ifdef _OPENMP
+            int t = omp_get_thread_num();
+#else
+            int t = 0;
+#endif
+            int64_t lo = n * t / T, hi = n * (t + 1) / T;
+            orc_heap hp[16];
+            for (int j = 0; j < qb; ++j) {
+                hp[j].h = store + ((size_t)t * QB + j) * (size_t)k;
+                hp[j].k = k;
+                hp[j].n = 0;
+            }
+            for (int64_t r = lo; r < hi; ++r) {
+                const float* x = X + r * (int64_t)d;
+                for (int j = 0; j < qb; ++j) {
+                    const float* q = Q + (q0 + j) * (int64_t)d;
+                    float s = acc_mode ? dot_f64(q, x, d) : dot_f32(q, x, d);
+                    if (hp[j].n < k || hit_better(s, r + id_offset, hp[j].h[0].s, hp[j].h[0].id))
+                        heap_offer(&hp[j], s, r + id_offset);
+                }
+            }
+            for (int j = 0; j < qb; ++j) cnt[t * QB + j] = hp[j].n;
+        }
+        /* merge thread heaps (+ previous result) per query */
+        for (int j = 0; j < qb; ++j) {
+            size_t m = 0;
+            orc_hit* all = (orc_hit*)malloc(sizeof(orc_hit) * ((size_t)T + 1) * (size_t)k);
+            if (!all) {
+                free(cnt);
+                free(store);
+                return -1;
+            }
+            for (int t = 0; t < T; ++t) {
+                memcpy(all + m, store + ((size_t)t * QB + j) * (size_t)k,
+                       sizeof(orc_hit) * (size_t)cnt[t * QB + j]);
+                m += (size_t)cnt[t * QB + j];
+            }
+            if (merge) {
+                for (int i = 0; i < k; ++i) {
+                    int64_t id = I[(q0 + j) * (int64_t)k + i];
+                    if (id < 0) break;
+                    all[m].s = D[(q0 + j) * (int64_t)k + i];
+                    all[m].id = id;
+                    ++m;
+                }
+            }
+            qsort(all, m, sizeof(orc_hit), hit_cmp_desc);
+            for (int i = 0; i < k; ++i) {
+                if ((size_t)i < m) {
+                    D[(q0 + j) * (int64_t)k + i] = all[i].s;
+                    I[(q0 + j) * (int64_t)k + i] = all[i].id;
+                } else {
+                    D[(q0 + j) * (int64_t)k + i] = -FLT_MAX;
+                    I[(q0 + j) * (int64_t)k + i] = -1;
+                }
+            }
+            free(all);
+        }
+        free(cnt);
+    }
+    free(store);
+    return 0;
+}
+
+/* Full similarity matrix S[nq, n] = Q X^T (StudentModel.compute_similarity,
+ * pinned by /root/reference/tests/test_student_model.py:104-124). */
+ORC_API int orc_similarity(const float* X, int64_t n, int d, const float* Q, int64_t nq,
+                           int acc_mode, float* S) {
+    if (d <= 0 || n < 0 || nq < 0) return -1;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int64_t r = 0; r < n; ++r)
+        for (int64_t j = 0; j < nq; ++j)
+            S[j * n + r] = acc_mode ? dot_f64(Q + j * (int64_t)d, X + r * (int64_t)d, d)
+                                    : dot_f32(Q + j * (int64_t)d, X + r * (int64_t)d, d);
+    return 0;
+}
+
+/* fp32 -> bf16 (round to nearest even) -> fp32, the storage rounding the
+ * device index applies.  NaN is passed through quietly. */
+ORC_API void orc_round_bf16(const float* in, float* out, int64_t count) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int64_t i = 0; i < count; ++i) {
+        uint32_t u;
+        memcpy(&u, in + i, 4);
+        if ((u & 0x7fffffffu) > 0x7f800000u) {
+            u |= 0x00400000u;
+            u &= 0xffff0000u;
+        } else {
+            uint32_t lsb = (u >> 16) & 1u;
+            u += 0x7fffu + lsb;
+            u &= 0xffff0000u;
+        }
+        memcpy(out + i, &u, 4);
+    }
+}
+
+/* fp32 -> raw bf16 bit patterns (uint16), same rounding. */
+ORC_API void orc_to_bf16_bits(const float* in, uint16_t* out, int64_t count) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int64_t i = 0; i < count; ++i) {
+        uint32_t u;
+        memcpy(&u, in + i, 4);
+        if ((u & 0x7fffffffu) > 0x7f800000u) {
+            u |= 0x00400000u;
+        } else {
+            uint32_t lsb = (u >> 16) & 1u;
+            u += 0x7fffu + lsb;
+        }
+        out[i] = (uint16_t)(u >> 16);
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* synthetic unit-norm rows for the CPU baseline legs of bench.py      */
+/* (counter-based, any row reproducible independently; NOT used for     */
+/* parity -- parity inputs are generated once and shared bit-for-bit).  */
+/* ------------------------------------------------------------------ */
+
+static inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+ORC_API void orc_gen_unit_rows(float* out, int64_t n, int d, uint64_t seed, int64_t row_offset) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int64_t r = 0; r < n; ++r) {
+        float* row = out + r * (int64_t)d;
+        uint64_t base = splitmix64(seed ^ (uint64_t)(r + row_offset) * 0xD1342543DE82EF95ull);
+        double ss = 0.0;
+        for (int i = 0; i < d; i += 2) {
+            uint64_t u = splitmix64(base + (uint64_t)i);
+            /* Box-Muller on two 32-bit uniforms */
+            double u1 = ((double)(uint32_t)(u >> 32) + 1.0) * (1.0 / 4294967297.0);
+            double u2 = ((double)(uint32_t)u) * (1.0 / 4294967296.0);
+            double rad = sqrt(-2.0 * log(u1));
+            double a = rad * cos(6.283185307179586 * u2);
+            double b = rad * sin(6.283185307179586 * u2);
+            row[i] = (float)a;
+            ss += a * a;
+            if (i + 1 < d) {
+                row[i + 1] = (float)b;
+                ss += b * b;
+            }
+        }
+        float inv = (float)(1.0 / sqrt(ss > 0 ? ss : 1.0));
+        for (int i = 0; i < d; ++i) row[i] *= inv;
+    }
+}
+
+ORC_API int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

@@ -1,0 +1,744 @@
+// b2s_api.cu -- C-ABI entry points of libb200search.so (see include/b200search.h).
+//
+// Host side of the exact inner-product top-k path: owns the bf16 corpus shard in HBM, sizes the
+// workspace, picks the kernel family (K1 scan for tiny batches, K2 tcgen05 GEMM for real
+// batches), launches the final per-query merge (K3) and moves host buffers for the host API.
+// There is NO CPU fallback: without an sm_100 device every compute entry point returns
+// B2S_ERR_NO_DEVICE.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "../../include/b200search.h"
+#include "merge_topk.cuh"
+#include "scan_topk.cuh"
+#include "select.cuh"
+#include "util_kernels.cuh"
+#ifndef B2S_NO_TENSOR_PATH
+#include "gemm_topk_tc.cuh"
+#endif
+
+using namespace b2s;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            int _code = (_e == cudaErrorMemoryAllocation) ? B2S_ERR_NOMEM : B2S_ERR_CUDA;        \
+            if (_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver) _code = B2S_ERR_NO_DEVICE; \
+            return fail(_code, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+        }                                                                                       \
+    } while (0)
+
+constexpr int kMaxK = 2048;
+constexpr int kScanQueryChunk = 64;   // queries per workspace round on the scan path
+constexpr int kSeedUnitStride = 64;   // the seeding pre-pass reads every 64th unit (~1.6% of rows)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return B2S_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        size_t want = need + need / 4;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&p, need);
+            want = need;
+        }
+        if (e != cudaSuccess) {
+            p = nullptr;
+            cudaGetLastError();
+            return fail(B2S_ERR_NOMEM, std::string("cudaMalloc workspace: ") + cudaGetErrorString(e));
+        }
+        bytes = want;
+        return B2S_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+}  // namespace
+
+struct b2s_index {
+    int dim = 0;
+    int metric = 0;
+    int device = 0;
+    int num_sms = 0;
+    __nv_bfloat16* rows = nullptr;  // [cap_rows, dim]
+    float* rows_f32 = nullptr;      // optional fp32 copy (keep_f32)
+    int64_t n = 0;
+    int64_t cap_rows = 0;
+    int64_t id_offset = 0;
+    // options
+    int opt_path = B2S_PATH_AUTO;
+    int opt_seed = -1;
+    int opt_scan_ctas_per_sm = 2;
+    int opt_keep_f32 = 0;
+    int opt_rescore_pad = 32;
+    int opt_timing = 0;
+    int opt_tc_min_nq = 5;
+    // workspace
+    DevBuf ws_lists, ws_counts, ws_seed, ws_qf32, ws_qbf16, ws_io_q, ws_io_scores, ws_io_ids, ws_tmp;
+    void* pin_q = nullptr;
+    void* pin_out = nullptr;
+    size_t pin_q_bytes = 0, pin_out_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+    b2s_stats stats;
+    std::mutex mu;
+#ifndef B2S_NO_TENSOR_PATH
+    TensorPathState tc;
+#endif
+};
+
+namespace {
+
+int use_device(const b2s_index* idx) {
+    CUDA_TRY(cudaSetDevice(idx->device));
+    return B2S_OK;
+}
+
+int grow_rows(b2s_index* idx, int64_t need_rows) {
+    if (need_rows <= idx->cap_rows) return B2S_OK;
+    int64_t new_cap = std::max<int64_t>(need_rows, idx->cap_rows + idx->cap_rows / 2);
+    __nv_bfloat16* nr = nullptr;
+    const size_t row_bytes = (size_t)idx->dim * sizeof(__nv_bfloat16);
+    cudaError_t e = cudaMalloc((void**)&nr, (size_t)new_cap * row_bytes);
+    if (e != cudaSuccess && new_cap > need_rows) {
+        cudaGetLastError();
+        new_cap = need_rows;
+        e = cudaMalloc((void**)&nr, (size_t)new_cap * row_bytes);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(B2S_ERR_NOMEM, std::string("cudaMalloc corpus: ") + cudaGetErrorString(e));
+    }
+    if (idx->n > 0) CUDA_TRY(cudaMemcpy(nr, idx->rows, (size_t)idx->n * row_bytes, cudaMemcpyDeviceToDevice));
+    if (idx->rows) cudaFree(idx->rows);
+    idx->rows = nr;
+    if (idx->opt_keep_f32) {
+        float* nf = nullptr;
+        e = cudaMalloc((void**)&nf, (size_t)new_cap * idx->dim * sizeof(float));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(B2S_ERR_NOMEM, std::string("cudaMalloc fp32 corpus: ") + cudaGetErrorString(e));
+        }
+        if (idx->n > 0 && idx->rows_f32)
+            CUDA_TRY(cudaMemcpy(nf, idx->rows_f32, (size_t)idx->n * idx->dim * sizeof(float),
+                                cudaMemcpyDeviceToDevice));
+        if (idx->rows_f32) cudaFree(idx->rows_f32);
+        idx->rows_f32 = nf;
+    }
+    idx->cap_rows = new_cap;
+#ifndef B2S_NO_TENSOR_PATH
+    idx->tc.corpus_map_valid = false;
+#endif
+    return B2S_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 dispatch
+// ---------------------------------------------------------------------------------------------
+
+template <int CPL, int NQ, int U>
+int launch_scan_t(const ScanParams& p, int grid, cudaStream_t s) {
+    const size_t smem = (size_t)NQ * p.cap * sizeof(u64);
+    auto kern = scan_topk_kernel<CPL, NQ, U>;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kScanThreads, smem, s>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    return B2S_OK;
+}
+
+// Largest register-resident query count the scan kernel is built for at this dim.
+int scan_max_nq(int dim) {
+    const int cpl = dim / 128;
+    if (cpl <= 3) return 4;
+    if (cpl == 4) return 2;
+    return 1;
+}
+
+int scan_rows_per_iter(int dim) { return (dim / 128 <= 3) ? 8 : 4; }
+
+int launch_scan(int dim, int nq_group, const ScanParams& p, int grid, cudaStream_t s) {
+    const int cpl = dim / 128;
+#define B2S_SCAN_CASE(C, Q, UU) \
+    if (cpl == C && nq_group == Q) return launch_scan_t<C, Q, UU>(p, grid, s);
+    B2S_SCAN_CASE(1, 1, 4) B2S_SCAN_CASE(1, 2, 4) B2S_SCAN_CASE(1, 4, 4)
+    B2S_SCAN_CASE(2, 1, 4) B2S_SCAN_CASE(2, 2, 4) B2S_SCAN_CASE(2, 4, 4)
+    B2S_SCAN_CASE(3, 1, 4) B2S_SCAN_CASE(3, 2, 4) B2S_SCAN_CASE(3, 4, 4)
+    B2S_SCAN_CASE(4, 1, 2) B2S_SCAN_CASE(4, 2, 2)
+    B2S_SCAN_CASE(6, 1, 2)
+    B2S_SCAN_CASE(8, 1, 2)
+#undef B2S_SCAN_CASE
+    return fail(B2S_ERR_UNSUPPORTED, "scan kernel: unsupported (dim, query group)");
+}
+
+bool dim_supported(int dim) {
+    return dim == 128 || dim == 256 || dim == 384 || dim == 512 || dim == 768 || dim == 1024;
+}
+
+int launch_merge(const MergeParams& mp, int nq, cudaStream_t s) {
+    merge_topk_kernel<<<nq, kMergeThreads, 0, s>>>(mp);
+    CUDA_TRY(cudaGetLastError());
+    return B2S_OK;
+}
+
+// Scan path for queries [0, nq) already in fp32 on the device.
+int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* out_scores,
+                int64_t* out_ids, cudaStream_t s, bool seed) {
+    const int cap = list_capacity(k);
+    const int rpi = scan_rows_per_iter(idx->dim);
+    const int unit = rpi * kScanWarps;
+    int grid = idx->num_sms * std::max(1, idx->opt_scan_ctas_per_sm);
+    const int64_t units = (idx->n + unit - 1) / unit;
+    if ((int64_t)grid > units) grid = (int)units;
+    const int64_t rows_per_cta = ((units + grid - 1) / grid) * unit;
+    grid = (int)((idx->n + rows_per_cta - 1) / rows_per_cta);
+    const int max_group = scan_max_nq(idx->dim);
+
+    const int chunk = (int)std::min<int64_t>(nq, kScanQueryChunk);
+    int rc;
+    if ((rc = idx->ws_lists.ensure((size_t)grid * chunk * cap * sizeof(u64))) != B2S_OK) return rc;
+    if ((rc = idx->ws_counts.ensure((size_t)grid * chunk * sizeof(int))) != B2S_OK) return rc;
+    if (seed && (rc = idx->ws_seed.ensure((size_t)chunk * sizeof(u64))) != B2S_OK) return rc;
+
+    for (int64_t c0 = 0; c0 < nq; c0 += chunk) {
+        const int cn = (int)std::min<int64_t>(chunk, nq - c0);
+        for (int pass = seed ? 0 : 1; pass < 2; ++pass) {
+            for (int g0 = 0; g0 < cn;) {
+                int group = 1;
+                while (group * 2 <= max_group && g0 + group * 2 <= cn) group *= 2;
+                ScanParams p;
+                p.corpus = reinterpret_cast<const uint4*>(idx->rows);
+                p.queries = q_f32 + (size_t)c0 * idx->dim;
+                p.n_rows = idx->n;
+                p.rows_per_cta = rows_per_cta;
+                p.q_begin = g0;
+                p.nq_valid = group;
+                p.k = k;
+                p.cap = cap;
+                p.unit_stride = pass == 0 ? kSeedUnitStride : 1;
+                p.seed_keys = (pass == 1 && seed) ? reinterpret_cast<const u64*>(idx->ws_seed.p) : nullptr;
+                p.lists = reinterpret_cast<u64*>(idx->ws_lists.p);
+                p.counts = reinterpret_cast<int*>(idx->ws_counts.p);
+                p.nq_lists = chunk;
+                if ((rc = launch_scan(idx->dim, group, p, grid, s)) != B2S_OK) return rc;
+                idx->stats.kernel_launches++;
+                if (pass == 1) idx->stats.passes++;
+                g0 += group;
+            }
+            MergeParams mp;
+            memset(&mp, 0, sizeof(mp));
+            mp.lists = reinterpret_cast<const u64*>(idx->ws_lists.p);
+            mp.counts = reinterpret_cast<const int*>(idx->ws_counts.p);
+            mp.num_lists = grid;
+            mp.nq_lists = chunk;
+            mp.cap = cap;
+            mp.k = k;
+            mp.id_offset = idx->id_offset;
+            if (pass == 0) {
+                mp.out_kth_key = reinterpret_cast<u64*>(idx->ws_seed.p);
+            } else {
+                mp.out_scores = out_scores + (size_t)c0 * k;
+                mp.out_ids = reinterpret_cast<long long*>(out_ids) + (size_t)c0 * k;
+            }
+            if (pass == 1 && idx->opt_timing && c0 == 0) cudaEventRecord(idx->ev[2], s);
+            if ((rc = launch_merge(mp, cn, s)) != B2S_OK) return rc;
+            idx->stats.kernel_launches++;
+        }
+    }
+    return B2S_OK;
+}
+
+int search_impl(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, int k, float* out_scores,
+                int64_t* out_ids, cudaStream_t s) {
+    if (!idx) return fail(B2S_ERR_INVALID, "null index");
+    if (nq < 0 || k < 0) return fail(B2S_ERR_INVALID, "nq and k must be >= 0");
+    if (nq == 0 || k == 0) return B2S_OK;
+    if (!queries || !out_scores || !out_ids) return fail(B2S_ERR_INVALID, "null buffer");
+    if (q_dtype != B2S_DTYPE_F32 && q_dtype != B2S_DTYPE_BF16) return fail(B2S_ERR_INVALID, "bad q_dtype");
+    if (k > kMaxK) return fail(B2S_ERR_UNSUPPORTED, "k > 2048 is not supported by the fused select");
+    if (nq > (int64_t)1 << 24) return fail(B2S_ERR_UNSUPPORTED, "nq too large for one call");
+    int rc;
+    if ((rc = use_device(idx)) != B2S_OK) return rc;
+
+    memset(&idx->stats, 0, sizeof(idx->stats));
+    idx->stats.corpus_bytes = idx->n * (int64_t)idx->dim * 2;
+    if (idx->opt_timing) {
+        cudaEventRecord(idx->ev[0], s);
+        idx->ev_valid = true;
+    } else {
+        idx->ev_valid = false;
+    }
+
+    if (idx->n == 0) {
+        const long long cnt = (long long)nq * k;
+        fill_empty_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(out_scores, reinterpret_cast<long long*>(out_ids), cnt);
+        CUDA_TRY(cudaGetLastError());
+        idx->stats.kernel_launches++;
+        if (idx->opt_timing) {
+            cudaEventRecord(idx->ev[1], s);
+            cudaEventRecord(idx->ev[2], s);
+            cudaEventRecord(idx->ev[3], s);
+        }
+        return B2S_OK;
+    }
+
+    // kernel family
+    int path = idx->opt_path;
+#ifdef B2S_NO_TENSOR_PATH
+    path = B2S_PATH_SCAN;
+#else
+    if (path == B2S_PATH_AUTO) path = (nq >= idx->opt_tc_min_nq) ? B2S_PATH_TENSOR : B2S_PATH_SCAN;
+    if (path == B2S_PATH_TENSOR && !tensor_path_supported(idx->dim)) path = B2S_PATH_SCAN;
+#endif
+    idx->stats.path = path;
+    const bool normalize = idx->metric == B2S_METRIC_COSINE;
+    bool seed = idx->opt_seed == 1 || (idx->opt_seed < 0 && k >= 32 && idx->n >= (int64_t)1 << 20);
+    idx->stats.seeded = seed ? 1 : 0;
+
+    if (path == B2S_PATH_SCAN) {
+        const float* qf = reinterpret_cast<const float*>(queries);
+        if (q_dtype != B2S_DTYPE_F32 || normalize) {
+            if ((rc = idx->ws_qf32.ensure((size_t)nq * idx->dim * sizeof(float))) != B2S_OK) return rc;
+            const int warps = 8;
+            prep_queries_kernel<<<(unsigned)((nq + warps - 1) / warps), warps * 32, 0, s>>>(
+                queries, q_dtype == B2S_DTYPE_BF16, nq, nq, idx->dim, normalize ? 1 : 0,
+                reinterpret_cast<float*>(idx->ws_qf32.p), nullptr);
+            CUDA_TRY(cudaGetLastError());
+            idx->stats.kernel_launches++;
+            qf = reinterpret_cast<const float*>(idx->ws_qf32.p);
+        }
+        if (idx->opt_timing) cudaEventRecord(idx->ev[1], s);
+        rc = search_scan(idx, qf, nq, k, out_scores, out_ids, s, seed);
+        if (rc != B2S_OK) return rc;
+    } else {
+#ifndef B2S_NO_TENSOR_PATH
+        rc = search_tensor(idx, queries, q_dtype, nq, k, out_scores, out_ids, s, seed, normalize);
+        if (rc != B2S_OK) return rc;
+#endif
+    }
+    if (idx->opt_timing) cudaEventRecord(idx->ev[3], s);
+    return B2S_OK;
+}
+
+int ensure_pinned(void** p, size_t* have, size_t need) {
+    if (need <= *have) return B2S_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    *have = 0;
+    size_t want = std::max<size_t>(need, 1 << 16);
+    cudaError_t e = cudaMallocHost(p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *p = nullptr;
+        return fail(B2S_ERR_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    }
+    *have = want;
+    return B2S_OK;
+}
+
+}  // namespace
+
+#ifndef B2S_NO_TENSOR_PATH
+#include "gemm_topk_host.inl"
+#endif
+
+// =============================================================================================
+// extern "C"
+// =============================================================================================
+
+extern "C" {
+
+B2S_API int b2s_version(void) { return 100; }
+
+B2S_API const char* b2s_last_error(void) { return g_err.c_str(); }
+
+B2S_API int b2s_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+B2S_API int b2s_create(int dim, int metric, int device, b2s_index** out) {
+    if (!out) return fail(B2S_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (!dim_supported(dim))
+        return fail(B2S_ERR_UNSUPPORTED, "dim must be one of 128, 256, 384, 512, 768, 1024");
+    if (metric != B2S_METRIC_INNER_PRODUCT && metric != B2S_METRIC_COSINE)
+        return fail(B2S_ERR_INVALID, "metric must be B2S_METRIC_INNER_PRODUCT or B2S_METRIC_COSINE");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(B2S_ERR_NO_DEVICE, "no CUDA device: libb200search has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(B2S_ERR_INVALID, "device ordinal out of range");
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(B2S_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                           ", this library is built for sm_100a only");
+    CUDA_TRY(cudaSetDevice(device));
+    b2s_index* idx = new (std::nothrow) b2s_index();
+    if (!idx) return fail(B2S_ERR_NOMEM, "host allocation failed");
+    idx->dim = dim;
+    idx->metric = metric;
+    idx->device = device;
+    idx->num_sms = prop.multiProcessorCount;
+    memset(&idx->stats, 0, sizeof(idx->stats));
+    if (cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete idx;
+        return fail(B2S_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    for (int i = 0; i < 4; ++i) {
+        if (cudaEventCreate(&idx->ev[i]) != cudaSuccess) {
+            delete idx;
+            return fail(B2S_ERR_CUDA, "cudaEventCreate failed");
+        }
+    }
+    *out = idx;
+    return B2S_OK;
+}
+
+B2S_API int b2s_destroy(b2s_index* idx) {
+    if (!idx) return B2S_OK;
+    cudaSetDevice(idx->device);
+    cudaDeviceSynchronize();
+    if (idx->rows) cudaFree(idx->rows);
+    if (idx->rows_f32) cudaFree(idx->rows_f32);
+    idx->ws_lists.release();
+    idx->ws_counts.release();
+    idx->ws_seed.release();
+    idx->ws_qf32.release();
+    idx->ws_qbf16.release();
+    idx->ws_io_q.release();
+    idx->ws_io_scores.release();
+    idx->ws_io_ids.release();
+    idx->ws_tmp.release();
+#ifndef B2S_NO_TENSOR_PATH
+    tensor_path_release(idx);
+#endif
+    if (idx->pin_q) cudaFreeHost(idx->pin_q);
+    if (idx->pin_out) cudaFreeHost(idx->pin_out);
+    for (int i = 0; i < 4; ++i)
+        if (idx->ev[i]) cudaEventDestroy(idx->ev[i]);
+    if (idx->stream) cudaStreamDestroy(idx->stream);
+    cudaGetLastError();
+    delete idx;
+    return B2S_OK;
+}
+
+B2S_API int b2s_reserve(b2s_index* idx, int64_t n_rows) {
+    if (!idx || n_rows < 0) return fail(B2S_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> g(idx->mu);
+    int rc = use_device(idx);
+    if (rc != B2S_OK) return rc;
+    return grow_rows(idx, n_rows);
+}
+
+static int add_impl(b2s_index* idx, const void* rows, int64_t n, int is_device, bool is_bf16) {
+    if (!idx) return fail(B2S_ERR_INVALID, "null index");
+    if (n < 0) return fail(B2S_ERR_INVALID, "n < 0");
+    if (n == 0) return B2S_OK;
+    if (!rows) return fail(B2S_ERR_INVALID, "rows is null");
+    if (idx->n + n > 0x7fffffff) return fail(B2S_ERR_UNSUPPORTED, "more than 2^31-1 rows in one shard");
+    std::lock_guard<std::mutex> g(idx->mu);
+    int rc = use_device(idx);
+    if (rc != B2S_OK) return rc;
+    if ((rc = grow_rows(idx, idx->n + n)) != B2S_OK) return rc;
+    const int dim = idx->dim;
+    const size_t esz = is_bf16 ? 2 : 4;
+    const bool normalize = idx->metric == B2S_METRIC_COSINE;
+    const int64_t chunk_rows = std::max<int64_t>(1, ((int64_t)256 << 20) / ((int64_t)dim * (int64_t)esz));
+    for (int64_t r0 = 0; r0 < n; r0 += chunk_rows) {
+        const int64_t rn = std::min<int64_t>(chunk_rows, n - r0);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(rows) + (size_t)r0 * dim * esz;
+        const void* dsrc = src;
+        if (!is_device) {
+            if ((rc = idx->ws_tmp.ensure((size_t)rn * dim * esz)) != B2S_OK) return rc;
+            CUDA_TRY(cudaMemcpyAsync(idx->ws_tmp.p, src, (size_t)rn * dim * esz, cudaMemcpyHostToDevice, idx->stream));
+            dsrc = idx->ws_tmp.p;
+        }
+        __nv_bfloat16* dst = idx->rows + (size_t)(idx->n + r0) * dim;
+        const int warps = 8;
+        const unsigned blocks = (unsigned)((rn + warps - 1) / warps);
+        if (is_bf16) {
+            if (normalize) {
+                rows_bf16_normalize_kernel<<<blocks, warps * 32, 0, idx->stream>>>(
+                    reinterpret_cast<const __nv_bfloat16*>(dsrc), dst, rn, dim);
+                CUDA_TRY(cudaGetLastError());
+            } else {
+                CUDA_TRY(cudaMemcpyAsync(dst, dsrc, (size_t)rn * dim * 2, cudaMemcpyDeviceToDevice, idx->stream));
+            }
+            if (idx->opt_keep_f32 && idx->rows_f32) {
+                rows_bf16_to_f32_kernel<<<1024, 256, 0, idx->stream>>>(dst, idx->rows_f32 + (size_t)(idx->n + r0) * dim,
+                                                                      (long long)rn * dim);
+                CUDA_TRY(cudaGetLastError());
+            }
+        } else {
+            rows_f32_to_bf16_kernel<<<blocks, warps * 32, 0, idx->stream>>>(
+                reinterpret_cast<const float*>(dsrc), dst, rn, dim, normalize ? 1 : 0);
+            CUDA_TRY(cudaGetLastError());
+            if (idx->opt_keep_f32 && idx->rows_f32) {
+                // fp32 copy keeps the caller's values (normalised on the fly at re-score time if cosine)
+                CUDA_TRY(cudaMemcpyAsync(idx->rows_f32 + (size_t)(idx->n + r0) * dim, dsrc,
+                                         (size_t)rn * dim * sizeof(float), cudaMemcpyDeviceToDevice, idx->stream));
+            }
+        }
+        CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    }
+    idx->n += n;
+#ifndef B2S_NO_TENSOR_PATH
+    idx->tc.corpus_map_valid = false;
+#endif
+    return B2S_OK;
+}
+
+B2S_API int b2s_add_f32(b2s_index* idx, const float* rows, int64_t n, int is_device) {
+    return add_impl(idx, rows, n, is_device, false);
+}
+B2S_API int b2s_add_bf16(b2s_index* idx, const void* rows, int64_t n, int is_device) {
+    return add_impl(idx, rows, n, is_device, true);
+}
+
+B2S_API int64_t b2s_ntotal(const b2s_index* idx) { return idx ? idx->n : 0; }
+B2S_API int b2s_dim(const b2s_index* idx) { return idx ? idx->dim : 0; }
+
+B2S_API int b2s_reset(b2s_index* idx) {
+    if (!idx) return fail(B2S_ERR_INVALID, "null index");
+    std::lock_guard<std::mutex> g(idx->mu);
+    idx->n = 0;
+#ifndef B2S_NO_TENSOR_PATH
+    idx->tc.corpus_map_valid = false;
+#endif
+    return B2S_OK;
+}
+
+B2S_API int b2s_set_id_offset(b2s_index* idx, int64_t offset) {
+    if (!idx || offset < 0) return fail(B2S_ERR_INVALID, "bad arguments");
+    idx->id_offset = offset;
+    return B2S_OK;
+}
+
+B2S_API int b2s_set_option(b2s_index* idx, const char* name, int64_t value) {
+    if (!idx || !name) return fail(B2S_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> g(idx->mu);
+    const std::string s(name);
+    if (s == "path") {
+        if (value < 0 || value > 2) return fail(B2S_ERR_INVALID, "path must be 0, 1 or 2");
+        idx->opt_path = (int)value;
+    } else if (s == "seed") {
+        idx->opt_seed = (int)value;
+    } else if (s == "scan_ctas_per_sm") {
+        if (value < 1 || value > 8) return fail(B2S_ERR_INVALID, "scan_ctas_per_sm must be in [1, 8]");
+        idx->opt_scan_ctas_per_sm = (int)value;
+    } else if (s == "keep_f32") {
+        if (idx->n > 0 && value && !idx->opt_keep_f32)
+            return fail(B2S_ERR_INVALID, "keep_f32 must be set before the first add");
+        idx->opt_keep_f32 = value ? 1 : 0;
+    } else if (s == "rescore_pad") {
+        idx->opt_rescore_pad = (int)std::max<int64_t>(0, value);
+    } else if (s == "timing") {
+        idx->opt_timing = value ? 1 : 0;
+    } else if (s == "tc_min_nq") {
+        idx->opt_tc_min_nq = (int)std::max<int64_t>(1, value);
+    } else {
+        return fail(B2S_ERR_INVALID, "unknown option: " + s);
+    }
+    return B2S_OK;
+}
+
+B2S_API int64_t b2s_get_option(const b2s_index* idx, const char* name) {
+    if (!idx || !name) return -1;
+    const std::string s(name);
+    if (s == "path") return idx->opt_path;
+    if (s == "seed") return idx->opt_seed;
+    if (s == "scan_ctas_per_sm") return idx->opt_scan_ctas_per_sm;
+    if (s == "keep_f32") return idx->opt_keep_f32;
+    if (s == "rescore_pad") return idx->opt_rescore_pad;
+    if (s == "timing") return idx->opt_timing;
+    if (s == "tc_min_nq") return idx->opt_tc_min_nq;
+    if (s == "num_sms") return idx->num_sms;
+    return -1;
+}
+
+B2S_API int b2s_search_device(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, int k,
+                              float* out_scores, int64_t* out_ids, void* cuda_stream) {
+    if (!idx) return fail(B2S_ERR_INVALID, "null index");
+    std::lock_guard<std::mutex> g(idx->mu);
+    return search_impl(idx, queries, q_dtype, nq, k, out_scores, out_ids, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+B2S_API int b2s_search(b2s_index* idx, const float* queries, int64_t nq, int k, float* out_scores,
+                       int64_t* out_ids) {
+    if (!idx) return fail(B2S_ERR_INVALID, "null index");
+    if (nq < 0 || k < 0) return fail(B2S_ERR_INVALID, "nq and k must be >= 0");
+    if (nq == 0 || k == 0) return B2S_OK;
+    if (!queries || !out_scores || !out_ids) return fail(B2S_ERR_INVALID, "null buffer");
+    std::lock_guard<std::mutex> g(idx->mu);
+    int rc = use_device(idx);
+    if (rc != B2S_OK) return rc;
+    const size_t qbytes = (size_t)nq * idx->dim * sizeof(float);
+    const size_t sbytes = (size_t)nq * k * sizeof(float);
+    const size_t ibytes = (size_t)nq * k * sizeof(int64_t);
+    if ((rc = idx->ws_io_q.ensure(qbytes)) != B2S_OK) return rc;
+    if ((rc = idx->ws_io_scores.ensure(sbytes)) != B2S_OK) return rc;
+    if ((rc = idx->ws_io_ids.ensure(ibytes)) != B2S_OK) return rc;
+    const bool small = qbytes <= ((size_t)1 << 20) && (sbytes + ibytes) <= ((size_t)1 << 20);
+    if (small) {
+        // stage through pinned memory so that both copies are truly asynchronous DMA
+        if ((rc = ensure_pinned(&idx->pin_q, &idx->pin_q_bytes, qbytes)) != B2S_OK) return rc;
+        if ((rc = ensure_pinned(&idx->pin_out, &idx->pin_out_bytes, sbytes + ibytes)) != B2S_OK) return rc;
+        memcpy(idx->pin_q, queries, qbytes);
+        CUDA_TRY(cudaMemcpyAsync(idx->ws_io_q.p, idx->pin_q, qbytes, cudaMemcpyHostToDevice, idx->stream));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(idx->ws_io_q.p, queries, qbytes, cudaMemcpyHostToDevice, idx->stream));
+    }
+    rc = search_impl(idx, idx->ws_io_q.p, B2S_DTYPE_F32, nq, k, reinterpret_cast<float*>(idx->ws_io_scores.p),
+                     reinterpret_cast<int64_t*>(idx->ws_io_ids.p), idx->stream);
+    if (rc != B2S_OK) return rc;
+    if (small) {
+        unsigned char* po = reinterpret_cast<unsigned char*>(idx->pin_out);
+        CUDA_TRY(cudaMemcpyAsync(po, idx->ws_io_ids.p, ibytes, cudaMemcpyDeviceToHost, idx->stream));
+        CUDA_TRY(cudaMemcpyAsync(po + ibytes, idx->ws_io_scores.p, sbytes, cudaMemcpyDeviceToHost, idx->stream));
+        CUDA_TRY(cudaStreamSynchronize(idx->stream));
+        memcpy(out_ids, po, ibytes);
+        memcpy(out_scores, po + ibytes, sbytes);
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(out_ids, idx->ws_io_ids.p, ibytes, cudaMemcpyDeviceToHost, idx->stream));
+        CUDA_TRY(cudaMemcpyAsync(out_scores, idx->ws_io_scores.p, sbytes, cudaMemcpyDeviceToHost, idx->stream));
+        CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    }
+    return B2S_OK;
+}
+
+B2S_API int b2s_merge_device(int device, const float* scores, const int64_t* ids, int g, int64_t nq,
+                             int k, float* out_scores, int64_t* out_ids, void* cuda_stream) {
+    if (g < 1 || nq < 0 || k < 0) return fail(B2S_ERR_INVALID, "bad arguments");
+    if (nq == 0 || k == 0) return B2S_OK;
+    if (!scores || !ids || !out_scores || !out_ids) return fail(B2S_ERR_INVALID, "null buffer");
+    if ((int64_t)g * k > kMergeSortCap)
+        return fail(B2S_ERR_UNSUPPORTED, "g * k exceeds the merge buffer (4096 candidates per query)");
+    CUDA_TRY(cudaSetDevice(device));
+    MergeParams mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.k = k;
+    mp.in_scores = scores;
+    mp.in_ids = reinterpret_cast<const long long*>(ids);
+    mp.g = g;
+    mp.k_in = k;
+    mp.nq = nq;
+    mp.out_scores = out_scores;
+    mp.out_ids = reinterpret_cast<long long*>(out_ids);
+    merge_pairs_kernel<<<(unsigned)nq, kMergeThreads, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(mp);
+    CUDA_TRY(cudaGetLastError());
+    return B2S_OK;
+}
+
+B2S_API int b2s_similarity(int device, const float* q, int64_t nq, const float* d, int64_t nd, int dim,
+                           float* out) {
+    if (nq < 0 || nd < 0 || dim <= 0) return fail(B2S_ERR_INVALID, "bad arguments");
+    if (nq == 0 || nd == 0) return B2S_OK;
+    if (!q || !d || !out) return fail(B2S_ERR_INVALID, "null buffer");
+    if ((size_t)dim * 8 * sizeof(float) > 96 * 1024) return fail(B2S_ERR_UNSUPPORTED, "dim too large");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(B2S_ERR_NO_DEVICE, "no CUDA device: libb200search has no CPU fallback");
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    float *dq = nullptr, *dd = nullptr, *ds = nullptr;
+    int rc = B2S_OK;
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&dq, (size_t)nq * dim * 4)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&dd, (size_t)nd * dim * 4)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&ds, (size_t)nq * nd * 4)) != cudaSuccess) {
+        rc = fail(B2S_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    if (rc == B2S_OK) {
+        const size_t smem = (size_t)dim * 8 * sizeof(float);
+        e = cudaMemcpy(dq, q, (size_t)nq * dim * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(dd, d, (size_t)nd * dim * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && smem > 48 * 1024)
+            e = cudaFuncSetAttribute(similarity_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) {
+            similarity_f32_kernel<<<(unsigned)((nd + 7) / 8), 256, smem>>>(dq, nq, dd, nd, dim, ds);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpy(out, ds, (size_t)nq * nd * 4, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(B2S_ERR_CUDA, std::string("similarity: ") + cudaGetErrorString(e));
+    }
+    cudaFree(dq);
+    cudaFree(dd);
+    cudaFree(ds);
+    cudaGetLastError();
+    return rc;
+}
+
+B2S_API int b2s_read_rows_f32(b2s_index* idx, int64_t start, int64_t n, float* out_host) {
+    if (!idx || start < 0 || n < 0 || start + n > idx->n) return fail(B2S_ERR_INVALID, "row range out of bounds");
+    if (n == 0) return B2S_OK;
+    if (!out_host) return fail(B2S_ERR_INVALID, "null buffer");
+    std::lock_guard<std::mutex> g(idx->mu);
+    int rc = use_device(idx);
+    if (rc != B2S_OK) return rc;
+    const int64_t chunk_rows = std::max<int64_t>(1, ((int64_t)256 << 20) / ((int64_t)idx->dim * 4));
+    for (int64_t r0 = 0; r0 < n; r0 += chunk_rows) {
+        const int64_t rn = std::min<int64_t>(chunk_rows, n - r0);
+        if ((rc = idx->ws_tmp.ensure((size_t)rn * idx->dim * 4)) != B2S_OK) return rc;
+        rows_bf16_to_f32_kernel<<<1024, 256, 0, idx->stream>>>(idx->rows + (size_t)(start + r0) * idx->dim,
+                                                              reinterpret_cast<float*>(idx->ws_tmp.p),
+                                                              (long long)rn * idx->dim);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(out_host + (size_t)r0 * idx->dim, idx->ws_tmp.p, (size_t)rn * idx->dim * 4,
+                                 cudaMemcpyDeviceToHost, idx->stream));
+        CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    }
+    return B2S_OK;
+}
+
+B2S_API const void* b2s_rows_device(const b2s_index* idx) { return idx ? idx->rows : nullptr; }
+
+B2S_API int b2s_last_stats(const b2s_index* idx, b2s_stats* out) {
+    if (!idx || !out) return fail(B2S_ERR_INVALID, "bad arguments");
+    *out = idx->stats;
+    if (idx->ev_valid) {
+        // the caller must have synchronised the stream the search ran on
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, idx->ev[1], idx->ev[2]) == cudaSuccess) out->dominant_ms = ms;
+        if (cudaEventElapsedTime(&ms, idx->ev[0], idx->ev[3]) == cudaSuccess) out->total_ms = ms;
+        cudaGetLastError();
+    }
+    return B2S_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,209 @@
+// merge_topk.cuh -- K3/K4: per-query selection of the final top-k from candidate keys.
+//
+// Replaces faiss' heap_reorder / the reference's `np.argsort(scores)[::-1][:k]`
+// (/root/reference/src/kd/eval.py:86, scripts/simple_eval.py:35) on the (tiny) candidate set
+// that survives the fused per-CTA filters, and -- as K4 -- the cross-GPU merge of G sorted
+// local top-k lists after the all-gather.
+//
+// One CTA per query.  Candidates arrive as L segments of 64-bit keys (select.cuh).  If they fit
+// the shared-memory sort buffer they are gathered and bitonic-sorted; otherwise an MSB-first
+// 11-bit radix select over the segments narrows them to (winners + one bucket) that fits, then
+// the same sort finishes.  Keys are unique (row ids are unique), so the result is exact and
+// deterministic: scores descending, ties by ascending id, unfilled slots (-FLT_MAX, -1).
+#pragma once
+#include <float.h>
+#include "select.cuh"
+
+namespace b2s {
+
+constexpr int kMergeThreads = 512;
+constexpr int kMergeSortCap = 4096;  // keys (32 KB of shared memory)
+constexpr int kRadixBits = 11;
+constexpr int kRadixBins = 1 << kRadixBits;
+
+struct MergeParams {
+    const u64* lists;    // [L, nq_lists, cap]
+    const int* counts;   // [L, nq_lists]
+    int num_lists;       // L
+    int nq_lists;        // list stride in queries
+    int cap;
+    int k;
+    long long id_offset;  // added to decoded row ids
+    float* out_scores;    // [nq, k] or nullptr
+    long long* out_ids;   // [nq, k] or nullptr
+    u64* out_kth_key;     // optional [nq]: k-th best key (0 if fewer than k candidates) -- seeding
+    // K4 mode: candidates are (score, id) pairs instead of keys
+    const float* in_scores;    // [G, nq, k_in] or nullptr
+    const long long* in_ids;   // [G, nq, k_in]
+    int g;
+    int k_in;
+    long long nq;
+};
+
+__device__ __forceinline__ int next_pow2(int v) {
+    int p = 2;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// Block-wide: sort buf[0..m) descending (m <= kMergeSortCap), padding with 0 keys.
+__device__ __forceinline__ void block_sort_desc(u64* buf, int m, int tid) {
+    const int n = next_pow2(m);
+    for (int i = m + tid; i < n; i += kMergeThreads) buf[i] = 0ull;
+    __syncthreads();
+    bitonic_sort_desc(buf, n, tid, kMergeThreads, BlockSync());
+}
+
+__global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergeParams p) {
+    __shared__ u64 buf[kMergeSortCap];
+    __shared__ int hist[kRadixBins];
+    __shared__ int s_total;
+    __shared__ int s_fill;
+    __shared__ u64 s_prefix;      // selected high bits so far
+    __shared__ int s_bits_done;   // number of high bits fixed in s_prefix
+    __shared__ int s_k_rem;       // rank still to find inside the current bucket
+    __shared__ int s_bucket_cnt;  // candidates inside the current bucket
+
+    const int q = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int L = p.num_lists;
+
+    if (tid == 0) {
+        s_total = 0;
+        s_fill = 0;
+    }
+    __syncthreads();
+    // total candidate count
+    int local = 0;
+    for (int l = tid; l < L; l += kMergeThreads) local += p.counts[(size_t)l * p.nq_lists + q];
+    if (local) atomicAdd(&s_total, local);
+    __syncthreads();
+    const int M = s_total;
+    int m_sorted;  // number of valid keys in buf after the gather
+
+    if (M <= kMergeSortCap) {
+        // gather everything (order irrelevant: it is sorted next)
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int l = warp; l < L; l += kMergeThreads / 32) {
+            const int c = p.counts[(size_t)l * p.nq_lists + q];
+            if (c == 0) continue;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_fill, c);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const u64* src = p.lists + ((size_t)l * p.nq_lists + q) * p.cap;
+            for (int i = lane; i < c; i += 32) buf[base + i] = src[i];
+        }
+        __syncthreads();
+        m_sorted = M;
+    } else {
+        // MSB-first radix select of the k-th largest key
+        if (tid == 0) {
+            s_prefix = 0ull;
+            s_bits_done = 0;
+            s_k_rem = p.k;
+            s_bucket_cnt = M;
+        }
+        __syncthreads();
+        while (true) {
+            const int bits_done = s_bits_done;
+            const int k_rem = s_k_rem;
+            // stop when winners (k - k_rem) + bucket fit the sort buffer, or all bits are fixed
+            if ((p.k - k_rem) + s_bucket_cnt <= kMergeSortCap || bits_done >= 64) break;
+            const int nbits = (64 - bits_done) < kRadixBits ? (64 - bits_done) : kRadixBits;
+            const int shift = 64 - bits_done - nbits;
+            const u64 prefix = s_prefix;
+            for (int i = tid; i < kRadixBins; i += kMergeThreads) hist[i] = 0;
+            __syncthreads();
+            for (int l = 0; l < L; ++l) {
+                const int c = p.counts[(size_t)l * p.nq_lists + q];
+                const u64* src = p.lists + ((size_t)l * p.nq_lists + q) * p.cap;
+                for (int i = tid; i < c; i += kMergeThreads) {
+                    const u64 key = src[i];
+                    const bool in_bucket = bits_done == 0 || (key >> (64 - bits_done)) == prefix;
+                    if (in_bucket) atomicAdd(&hist[(int)((key >> shift) & ((1u << nbits) - 1u))], 1);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int acc = 0;
+                int b = (1 << nbits) - 1;
+                for (; b > 0; --b) {
+                    if (acc + hist[b] >= k_rem) break;
+                    acc += hist[b];
+                }
+                // bucket b holds the k_rem-th largest of the current bucket
+                s_prefix = (prefix << nbits) | (u64)b;
+                s_bits_done = bits_done + nbits;
+                s_k_rem = k_rem - acc;
+                s_bucket_cnt = hist[b];
+            }
+            __syncthreads();
+        }
+        // gather winners (prefix bits above the bucket) and the bucket itself
+        const int bits_done = s_bits_done;
+        const u64 prefix = s_prefix;
+        for (int l = 0; l < L; ++l) {
+            const int c = p.counts[(size_t)l * p.nq_lists + q];
+            const u64* src = p.lists + ((size_t)l * p.nq_lists + q) * p.cap;
+            for (int i = tid; i < c; i += kMergeThreads) {
+                const u64 key = src[i];
+                const bool take = bits_done == 0 || (key >> (64 - bits_done)) >= prefix;
+                if (take) {
+                    int pos = atomicAdd(&s_fill, 1);
+                    if (pos < kMergeSortCap) buf[pos] = key;
+                }
+            }
+        }
+        __syncthreads();
+        m_sorted = s_fill < kMergeSortCap ? s_fill : kMergeSortCap;
+    }
+
+    block_sort_desc(buf, m_sorted > 0 ? m_sorted : 1, tid);
+
+    const int kk = m_sorted < p.k ? m_sorted : p.k;
+    for (int i = tid; i < p.k; i += kMergeThreads) {
+        float s = -FLT_MAX;
+        long long id = -1;
+        if (i < kk) {
+            const u64 key = buf[i];
+            s = key_score(key);
+            id = (long long)key_row(key) + p.id_offset;
+        }
+        if (p.out_scores) p.out_scores[(size_t)q * p.k + i] = s;
+        if (p.out_ids) p.out_ids[(size_t)q * p.k + i] = id;
+    }
+    if (p.out_kth_key && tid == 0) p.out_kth_key[q] = (m_sorted >= p.k) ? buf[p.k - 1] : 0ull;
+}
+
+// K4: merge G sorted (score, id) lists of length k_in per query.  Position g*k_in + j is the
+// tie-break (lists are in ascending id-range order and internally ordered by ascending id among
+// equal scores), so the packed key keeps the global (score desc, id asc) order without 64-bit ids.
+__global__ void __launch_bounds__(kMergeThreads) merge_pairs_kernel(const MergeParams p) {
+    __shared__ u64 buf[kMergeSortCap];
+    const int q = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int total = p.g * p.k_in;  // host guarantees total <= kMergeSortCap
+    for (int i = tid; i < total; i += kMergeThreads) {
+        const int g = i / p.k_in, j = i - g * p.k_in;
+        const size_t src = ((size_t)g * p.nq + q) * p.k_in + j;
+        const long long id = p.in_ids[src];
+        buf[i] = id < 0 ? 0ull : make_key(p.in_scores[src], (uint32_t)i);
+    }
+    __syncthreads();
+    block_sort_desc(buf, total > 0 ? total : 1, tid);
+    for (int i = tid; i < p.k; i += kMergeThreads) {
+        float s = -FLT_MAX;
+        long long id = -1;
+        if (i < total && buf[i] != 0ull) {
+            const int pos = (int)key_row(buf[i]);
+            const int g = pos / p.k_in, j = pos - g * p.k_in;
+            const size_t src = ((size_t)g * p.nq + q) * p.k_in + j;
+            s = p.in_scores[src];
+            id = p.in_ids[src];
+        }
+        p.out_scores[(size_t)q * p.k + i] = s;
+        p.out_ids[(size_t)q * p.k + i] = id;
+    }
+}
+
+}  // namespace b2s

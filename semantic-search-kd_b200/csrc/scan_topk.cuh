@@ -1,0 +1,178 @@
+// scan_topk.cuh -- K1: small-batch (1..4 queries) exact inner-product scan with fused top-k.
+//
+// Replaces faiss Index.search at nq = 1 behind FAISSIndexBuilder.search
+// (/root/reference/src/serve/app.py:293-295) and the per-query full-row score + argsort of
+// /root/reference/src/kd/eval.py:75,86.
+//
+// HBM-bound: one pass over the bf16 corpus (dim*2 bytes per row), nothing written back but the
+// per-CTA candidate lists (<= capacity keys per query).  Mapping: a HALF-WARP owns one row; lane
+// l (0..15) reads the 16-byte chunks l, l+16, l+32, ... of that row with 128-bit
+// ld.global.nc.L1::no_allocate loads, so a warp instruction covers two rows x 256 contiguous bytes.
+// Each warp keeps U row-pairs (2U rows, U*CPL independent 16-byte loads per lane) in flight per
+// iteration.  bf16 -> fp32 is a shift / mask, products are accumulated in fp32 against the query
+// held in registers as fp32 (the query is NOT rounded to bf16 on this path), a 4-step xor-shuffle
+// finishes the dot product inside the half-warp.  Scores that reach the CTA's current k-th best
+// are appended to the shared-memory candidate list (select.cuh); everything else is dropped in
+// registers, so the [N] score vector never exists in memory.
+#pragma once
+#include "select.cuh"
+
+namespace b2s {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanWarps = kScanThreads / 32;
+
+struct ScanParams {
+    const uint4* corpus;   // bf16 rows, row-major, dim*2 bytes each (16-byte aligned)
+    const float* queries;  // fp32 [nq_total, dim]; this launch uses rows q_begin .. q_begin+NQ-1
+    long long n_rows;      // rows in the shard
+    long long rows_per_cta;  // multiple of the unit (2U rows * kScanWarps)
+    int q_begin;
+    int nq_valid;          // how many of the NQ register queries are real (others masked)
+    int k;
+    int cap;               // list capacity (power of two)
+    int unit_stride;       // 1 = every unit; S = every S-th unit (threshold-seeding pre-pass)
+    const u64* seed_keys;  // optional [nq_total] initial thresholds (0 = none), or nullptr
+    u64* lists;            // out [gridDim.x, nq_lists, cap]
+    int* counts;           // out [gridDim.x, nq_lists]
+    int nq_lists;          // stride (in queries) of the list arrays
+};
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ float dot8(const uint4& w, const float* q, float acc) {
+    acc = fmaf(__uint_as_float(w.x << 16), q[0], acc);
+    acc = fmaf(__uint_as_float(w.x & 0xffff0000u), q[1], acc);
+    acc = fmaf(__uint_as_float(w.y << 16), q[2], acc);
+    acc = fmaf(__uint_as_float(w.y & 0xffff0000u), q[3], acc);
+    acc = fmaf(__uint_as_float(w.z << 16), q[4], acc);
+    acc = fmaf(__uint_as_float(w.z & 0xffff0000u), q[5], acc);
+    acc = fmaf(__uint_as_float(w.w << 16), q[6], acc);
+    acc = fmaf(__uint_as_float(w.w & 0xffff0000u), q[7], acc);
+    return acc;
+}
+
+// CPL = 16-byte chunks per lane = dim / 128; NQ = queries held in registers; U = row pairs in flight.
+template <int CPL, int NQ, int U>
+__global__ void __launch_bounds__(kScanThreads, (NQ <= 2 ? 2 : 1))
+scan_topk_kernel(const ScanParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* entries = reinterpret_cast<u64*>(smem_raw);  // [NQ][cap]
+    __shared__ ListState lists[NQ];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int half = lane >> 4;
+    const int hl = lane & 15;
+    constexpr int kChunksPerRow = CPL * 16;  // uint4 per row
+    constexpr int kRowsPerIter = 2 * U;
+
+    if (tid < NQ) {
+        u64 seed = 0ull;
+        if (p.seed_keys != nullptr && tid < p.nq_valid) seed = p.seed_keys[p.q_begin + tid];
+        list_init(&lists[tid], seed);
+        if (tid >= p.nq_valid) {  // masked query slot: nothing can pass
+            lists[tid].thr_key = ~0ull;
+            lists[tid].thr = INFINITY;
+        }
+    }
+
+    // query -> registers (fp32): lane hl keeps elements [(hl + 16 j) * 8, +8) for j < CPL
+    float qreg[NQ][CPL][8];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const int qi = p.q_begin + (q < p.nq_valid ? q : 0);
+        const float4* qp = reinterpret_cast<const float4*>(p.queries + (size_t)qi * (CPL * 128));
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            float4 a = __ldg(qp + (hl + 16 * j) * 2);
+            float4 b = __ldg(qp + (hl + 16 * j) * 2 + 1);
+            qreg[q][j][0] = a.x; qreg[q][j][1] = a.y; qreg[q][j][2] = a.z; qreg[q][j][3] = a.w;
+            qreg[q][j][4] = b.x; qreg[q][j][5] = b.y; qreg[q][j][6] = b.z; qreg[q][j][7] = b.w;
+        }
+    }
+    __syncthreads();
+
+    const long long row_begin = (long long)blockIdx.x * p.rows_per_cta;
+    long long row_end = row_begin + p.rows_per_cta;
+    if (row_end > p.n_rows) row_end = p.n_rows;
+    const long long last_row = p.n_rows - 1;
+
+    const long long step = (long long)kScanWarps * kRowsPerIter * p.unit_stride;
+    for (long long base = row_begin + (long long)warp * kRowsPerIter * p.unit_stride; base < row_end;
+         base += step) {
+        uint4 w[U][CPL];
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+            long long r = base + 2 * i + half;
+            if (r > last_row) r = last_row;  // clamp: loads stay in bounds, masked below
+            const uint4* rp = p.corpus + r * kChunksPerRow + hl;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) w[i][j] = ldg_stream(rp + 16 * j);
+        }
+        float acc[NQ][U];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+                float a = 0.f;
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) a = dot8(w[i][j], qreg[q][j], a);
+                acc[q][i] = a;
+            }
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                for (int i = 0; i < U; ++i) acc[q][i] += __shfl_xor_sync(0xffffffffu, acc[q][i], off);
+
+        // lane hl (< U) of each half-warp speaks for row base + 2*hl + half
+        const long long myrow = base + 2 * hl + half;
+        const bool row_ok = (hl < U) && (myrow < row_end);
+        bool any = false;
+        float mys[NQ];
+        bool pass[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            float s = acc[q][0];
+#pragma unroll
+            for (int i = 1; i < U; ++i) s = (hl == i) ? acc[q][i] : s;
+            mys[q] = s;
+            pass[q] = row_ok && (s >= *(volatile float*)&lists[q].thr);
+            any = any || pass[q];
+        }
+        if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                if (__any_sync(0xffffffffu, pass[q])) {
+                    list_append_warp(&lists[q], entries + (size_t)q * p.cap, p.cap, p.k, pass[q],
+                                     make_key(mys[q], (uint32_t)myrow), lane);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // final: leave exactly min(count, k) best keys per query, then publish
+    for (int q = warp; q < NQ; q += kScanWarps) {
+        if (*(volatile int*)&lists[q].count > p.k)
+            list_compact_warp(&lists[q], entries + (size_t)q * p.cap, p.cap, p.k, lane);
+    }
+    __syncthreads();
+    for (int q = 0; q < p.nq_valid; ++q) {
+        const int c = lists[q].count;
+        u64* dst = p.lists + ((size_t)blockIdx.x * p.nq_lists + (p.q_begin + q)) * p.cap;
+        for (int i = tid; i < c; i += kScanThreads) dst[i] = entries[(size_t)q * p.cap + i];
+        if (tid == 0) p.counts[(size_t)blockIdx.x * p.nq_lists + (p.q_begin + q)] = c;
+    }
+}
+
+}  // namespace b2s

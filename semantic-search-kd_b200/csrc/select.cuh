@@ -1,0 +1,144 @@
+// select.cuh -- candidate keys, threshold-filtered candidate lists and bitonic sorting.
+//
+// Every score that can still belong to a query's top-k is packed into ONE sortable 64-bit key:
+//      key = (order_preserving_u32(score) << 32) | ~local_row_id
+// so "larger key" == "higher score, then LOWER id" -- the (score desc, id asc) order of the
+// oracle (oracle/flat_ip.c: hit_better) and the earlier-id-survives rule of faiss' strict '>'
+// heap replacement.  All selection below is integer work on these keys and is bit-exact.
+//
+// A candidate list is a small array of keys owned by one CTA for one query, guarded by a spin
+// lock in shared memory.  Rows whose score reaches the list's threshold are appended by the
+// whole warp (ballot-compacted); when the list is full one warp sorts it, keeps the best k and
+// raises the threshold to the k-th key.  On unit-norm embedding data the survivor rate after
+// warm-up is ~k/rows_seen, so this path is cold; it is written for correctness on adversarial
+// inputs (sorted scores, all-equal scores), not for speed.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2s {
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ uint32_t score_to_ord(float s) {
+    s = s + 0.0f;  // -0.0 -> +0.0 so that equal scores have equal keys
+    uint32_t u = __float_as_uint(s);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_to_score(uint32_t o) {
+    uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ u64 make_key(float s, uint32_t row) {
+    return ((u64)score_to_ord(s) << 32) | (u64)(~row);
+}
+__device__ __forceinline__ float key_score(u64 key) { return ord_to_score((uint32_t)(key >> 32)); }
+__device__ __forceinline__ uint32_t key_row(u64 key) { return ~(uint32_t)key; }
+
+// Smallest power of two >= max(2k, k + 64): room for one full warp of appends after a
+// compaction, and at least a doubling of rows seen between compactions.
+__host__ __device__ inline int list_capacity(int k) {
+    int need = 2 * k > k + 64 ? 2 * k : k + 64;
+    int c = 64;
+    while (c < need) c <<= 1;
+    return c;
+}
+
+// In-place bitonic sort, DESCENDING, of a[0..n) (n a power of two) by `nthreads` cooperating
+// threads with ids tid in [0, nthreads).  `sync` is __syncwarp or __syncthreads.
+template <typename SyncFn>
+__device__ __forceinline__ void bitonic_sort_desc(u64* a, int n, int tid, int nthreads, SyncFn sync) {
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < (n >> 1); i += nthreads) {
+                int lo = 2 * i - (i & (stride - 1));
+                int hi = lo + stride;
+                bool desc = (lo & size) == 0;
+                u64 x = a[lo], y = a[hi];
+                if ((x < y) == desc) {
+                    a[lo] = y;
+                    a[hi] = x;
+                }
+            }
+            sync();
+        }
+    }
+}
+
+struct WarpSync {
+    __device__ __forceinline__ void operator()() const { __syncwarp(); }
+};
+struct BlockSync {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+// Per-(CTA, query) list state kept in shared memory.
+struct ListState {
+    u64 thr_key;   // a candidate must have key > thr_key
+    float thr;     // fast test: score >= thr   (score of thr_key, -inf when unset)
+    int count;     // entries currently in the list
+    int lock;      // 0 free, 1 held
+    int pad;
+};
+
+__device__ __forceinline__ void list_init(ListState* st, u64 seed_key) {
+    st->thr_key = seed_key;
+    st->thr = seed_key ? key_score(seed_key) : -INFINITY;
+    st->count = 0;
+    st->lock = 0;
+    st->pad = 0;
+}
+
+// One warp sorts entries[0..cap) (entries beyond count are zeroed first), keeps the best k and
+// publishes the new threshold.  Caller holds the lock.  Returns the new count.
+__device__ __forceinline__ int list_compact_warp(ListState* st, u64* entries, int cap, int k, int lane) {
+    int c = *(volatile int*)&st->count;
+    for (int i = c + lane; i < cap; i += 32) entries[i] = 0ull;
+    __syncwarp();
+    bitonic_sort_desc(entries, cap, lane, 32, WarpSync());
+    int keep = c < k ? c : k;
+    if (lane == 0) {
+        if (c >= k) {
+            u64 kth = entries[k - 1];
+            *(volatile u64*)&st->thr_key = kth;
+            *(volatile float*)&st->thr = key_score(kth);
+        }
+        *(volatile int*)&st->count = keep;
+    }
+    __syncwarp();
+    return keep;
+}
+
+// Warp-collective append.  Every lane of the warp calls it (converged); `pass` says whether this
+// lane offers `key`.  entries has `cap` slots (shared or global memory).
+__device__ __forceinline__ void list_append_warp(ListState* st, u64* entries, int cap, int k, bool pass,
+                                                 u64 key, int lane) {
+    if (lane == 0) {
+        while (atomicCAS(&st->lock, 0, 1) != 0) __nanosleep(32);
+    }
+    __syncwarp();
+    __threadfence_block();
+    u64 tk = *(volatile u64*)&st->thr_key;
+    pass = pass && (key > tk);
+    unsigned m = __ballot_sync(0xffffffffu, pass);
+    int n = __popc(m);
+    if (n) {
+        int c = *(volatile int*)&st->count;
+        if (c + n > cap) {
+            c = list_compact_warp(st, entries, cap, k, lane);
+            tk = *(volatile u64*)&st->thr_key;
+            pass = pass && (key > tk);
+            m = __ballot_sync(0xffffffffu, pass);
+            n = __popc(m);
+        }
+        if (pass) entries[c + __popc(m & ((1u << lane) - 1u))] = key;
+        __syncwarp();
+        if (lane == 0) *(volatile int*)&st->count = c + n;
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) atomicExch(&st->lock, 0);
+    __syncwarp();
+}
+
+}  // namespace b2s
