@@ -133,6 +133,16 @@ B2S_API int b2s_merge_device(int device, const float* scores, const int64_t* ids
                              int k, float* out_scores, int64_t* out_ids, void* cuda_stream);
 
 /*
+ * Same merge for the PACKED candidate block one all-gather moves per rank:
+ *   [ids int64 nq*k][scores float32 nq*k], padded to b2s_packed_bytes(nq, k).
+ * packed: device [g][b2s_packed_bytes].  A per-shard search writes straight into the views
+ * (ids at offset 0, scores at offset nq*k*8) of its own block.
+ */
+B2S_API int64_t b2s_packed_bytes(int64_t nq, int k);
+B2S_API int b2s_merge_packed_device(int device, const void* packed, int g, int64_t nq, int k,
+                                    float* out_scores, int64_t* out_ids, void* cuda_stream);
+
+/*
  * Replaces StudentModel.compute_similarity(q, d) -> [nq, nd]
  *   tests/test_student_model.py:104-124; src/mining/miners.py:228-233;
  *   src/kd/eval.py:75.  HOST fp32 buffers, out [nq, nd] row-major.
@@ -147,6 +157,13 @@ B2S_API int b2s_read_rows_f32(b2s_index* idx, int64_t start, int64_t n, float* o
 B2S_API const void* b2s_rows_device(const b2s_index* idx);
 
 B2S_API int b2s_last_stats(const b2s_index* idx, b2s_stats* out);
+
+/*
+ * With option "timing" = 1 every search records CUDA events around its dominant kernel(s) and
+ * around the whole call on the stream it runs on.  After synchronising that stream, read the
+ * last (up to max_n, ring of 4096) calls' device times in ms, oldest first.  Returns the count.
+ */
+B2S_API int b2s_read_timings(const b2s_index* idx, float* dominant_ms, float* total_ms, int max_n);
 
 #ifdef __cplusplus
 }

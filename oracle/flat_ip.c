@@ -310,27 +310,21 @@ static inline uint64_t splitmix64(uint64_t x) {
 }
 
 ORC_API void orc_gen_unit_rows(float* out, int64_t n, int d, uint64_t seed, int64_t row_offset) {
+    /* entries ~ Irwin-Hall(4) of 16-bit uniforms (near-normal, no transcendental), rows L2-normalised */
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static)
 #endif
     for (int64_t r = 0; r < n; ++r) {
         float* row = out + r * (int64_t)d;
-        uint64_t base = splitmix64(seed ^ (uint64_t)(r + row_offset) * 0xD1342543DE82EF95ull);
+        uint64_t base = splitmix64(seed ^ ((uint64_t)(r + row_offset) * 0xD1342543DE82EF95ull));
         double ss = 0.0;
-        for (int i = 0; i < d; i += 2) {
+        for (int i = 0; i < d; ++i) {
             uint64_t u = splitmix64(base + (uint64_t)i);
-            /* Box-Muller on two 32-bit uniforms */
-            double u1 = ((double)(uint32_t)(u >> 32) + 1.0) * (1.0 / 4294967297.0);
-            double u2 = ((double)(uint32_t)u) * (1.0 / 4294967296.0);
-            double rad = sqrt(-2.0 * log(u1));
-            double a = rad * cos(6.283185307179586 * u2);
-            double b = rad * sin(6.283185307179586 * u2);
-            row[i] = (float)a;
-            ss += a * a;
-            if (i + 1 < d) {
-                row[i + 1] = (float)b;
-                ss += b * b;
-            }
+            int v = (int)(u & 0xffff) + (int)((u >> 16) & 0xffff) + (int)((u >> 32) & 0xffff) +
+                    (int)((u >> 48) & 0xffff) - 2 * 65535;
+            float a = (float)v * (1.0f / 37837.0f); /* unit variance: sqrt(4/12) * 65536 */
+            row[i] = a;
+            ss += (double)a * (double)a;
         }
         float inv = (float)(1.0 / sqrt(ss > 0 ? ss : 1.0));
         for (int i = 0; i < d; ++i) row[i] *= inv;

@@ -36,7 +36,8 @@ EXPORTS = [
     "b2s_version", "b2s_last_error", "b2s_device_count", "b2s_create", "b2s_destroy", "b2s_reserve",
     "b2s_add_f32", "b2s_add_bf16", "b2s_ntotal", "b2s_dim", "b2s_reset", "b2s_set_id_offset",
     "b2s_set_option", "b2s_get_option", "b2s_search", "b2s_search_device", "b2s_merge_device",
-    "b2s_similarity", "b2s_read_rows_f32", "b2s_rows_device", "b2s_last_stats",
+    "b2s_similarity", "b2s_read_rows_f32", "b2s_rows_device", "b2s_last_stats", "b2s_read_timings",
+    "b2s_packed_bytes", "b2s_merge_packed_device",
 ]
 
 
@@ -122,6 +123,12 @@ def lib() -> ctypes.CDLL:
     L.b2s_rows_device.argtypes = [vp]
     L.b2s_rows_device.restype = vp
     L.b2s_last_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    L.b2s_read_timings.argtypes = [vp, vp, vp, i32]
+    L.b2s_read_timings.restype = i32
+    L.b2s_packed_bytes.argtypes = [i64, i32]
+    L.b2s_packed_bytes.restype = i64
+    L.b2s_merge_packed_device.argtypes = [i32, vp, i32, i64, i32, vp, vp, vp]
+    L.b2s_merge_packed_device.restype = i32
     for name in ("b2s_create", "b2s_destroy", "b2s_reserve", "b2s_add_f32", "b2s_add_bf16", "b2s_dim",
                  "b2s_reset", "b2s_set_id_offset", "b2s_set_option", "b2s_search", "b2s_search_device",
                  "b2s_merge_device", "b2s_similarity", "b2s_read_rows_f32", "b2s_last_stats"):

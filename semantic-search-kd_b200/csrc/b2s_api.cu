@@ -49,6 +49,7 @@ int fail(int code, const std::string& msg) {
 constexpr int kMaxK = 2048;
 constexpr int kScanQueryChunk = 64;   // queries per workspace round on the scan path
 constexpr int kSeedUnitStride = 64;   // the seeding pre-pass reads every 64th unit (~1.6% of rows)
+constexpr int kTimingSlots = 4096;    // search calls remembered by the timing ring
 
 struct DevBuf {
     void* p = nullptr;
@@ -106,7 +107,10 @@ struct b2s_index {
     void* pin_out = nullptr;
     size_t pin_q_bytes = 0, pin_out_bytes = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // timing ring: per search call, events [total begin, dominant begin, dominant end, total end]
+    cudaEvent_t* ring = nullptr;   // kTimingSlots * 4 events, created when "timing" is switched on
+    cudaEvent_t* ev = nullptr;     // the 4 events of the current call
+    int64_t ring_calls = 0;        // search calls recorded since timing was switched on
     bool ev_valid = false;
     b2s_stats stats;
     std::mutex mu;
@@ -289,10 +293,13 @@ int search_impl(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, in
 
     memset(&idx->stats, 0, sizeof(idx->stats));
     idx->stats.corpus_bytes = idx->n * (int64_t)idx->dim * 2;
-    if (idx->opt_timing) {
+    if (idx->opt_timing && idx->ring) {
+        idx->ev = idx->ring + 4 * (idx->ring_calls % kTimingSlots);
+        idx->ring_calls++;
         cudaEventRecord(idx->ev[0], s);
         idx->ev_valid = true;
     } else {
+        idx->opt_timing = 0;
         idx->ev_valid = false;
     }
 
@@ -419,12 +426,6 @@ B2S_API int b2s_create(int dim, int metric, int device, b2s_index** out) {
         delete idx;
         return fail(B2S_ERR_CUDA, "cudaStreamCreate failed");
     }
-    for (int i = 0; i < 4; ++i) {
-        if (cudaEventCreate(&idx->ev[i]) != cudaSuccess) {
-            delete idx;
-            return fail(B2S_ERR_CUDA, "cudaEventCreate failed");
-        }
-    }
     *out = idx;
     return B2S_OK;
 }
@@ -449,8 +450,11 @@ B2S_API int b2s_destroy(b2s_index* idx) {
 #endif
     if (idx->pin_q) cudaFreeHost(idx->pin_q);
     if (idx->pin_out) cudaFreeHost(idx->pin_out);
-    for (int i = 0; i < 4; ++i)
-        if (idx->ev[i]) cudaEventDestroy(idx->ev[i]);
+    if (idx->ring) {
+        for (int i = 0; i < 4 * kTimingSlots; ++i)
+            if (idx->ring[i]) cudaEventDestroy(idx->ring[i]);
+        delete[] idx->ring;
+    }
     if (idx->stream) cudaStreamDestroy(idx->stream);
     cudaGetLastError();
     delete idx;
@@ -568,7 +572,16 @@ B2S_API int b2s_set_option(b2s_index* idx, const char* name, int64_t value) {
     } else if (s == "rescore_pad") {
         idx->opt_rescore_pad = (int)std::max<int64_t>(0, value);
     } else if (s == "timing") {
+        if (value && !idx->ring) {
+            int rc = use_device(idx);
+            if (rc != B2S_OK) return rc;
+            idx->ring = new (std::nothrow) cudaEvent_t[4 * kTimingSlots]();
+            if (!idx->ring) return fail(B2S_ERR_NOMEM, "host allocation failed");
+            for (int i = 0; i < 4 * kTimingSlots; ++i) CUDA_TRY(cudaEventCreate(&idx->ring[i]));
+        }
         idx->opt_timing = value ? 1 : 0;
+        idx->ring_calls = 0;
+        idx->ev_valid = false;
     } else if (s == "tc_min_nq") {
         idx->opt_tc_min_nq = (int)std::max<int64_t>(1, value);
     } else {
@@ -657,6 +670,8 @@ B2S_API int b2s_merge_device(int device, const float* scores, const int64_t* ids
     mp.g = g;
     mp.k_in = k;
     mp.nq = nq;
+    mp.g_stride_ids = (long long)nq * k;
+    mp.g_stride_scores = (long long)nq * k;
     mp.out_scores = out_scores;
     mp.out_ids = reinterpret_cast<long long*>(out_ids);
     merge_pairs_kernel<<<(unsigned)nq, kMergeThreads, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(mp);
@@ -724,6 +739,57 @@ B2S_API int b2s_read_rows_f32(b2s_index* idx, int64_t start, int64_t n, float* o
         CUDA_TRY(cudaStreamSynchronize(idx->stream));
     }
     return B2S_OK;
+}
+
+B2S_API int b2s_read_timings(const b2s_index* idx, float* dominant_ms, float* total_ms, int max_n) {
+    if (!idx || max_n < 0) return fail(B2S_ERR_INVALID, "bad arguments");
+    if (!idx->ring) return 0;
+    const int64_t have = std::min<int64_t>(idx->ring_calls, kTimingSlots);
+    const int n = (int)std::min<int64_t>(have, max_n);
+    for (int i = 0; i < n; ++i) {
+        const int64_t call = idx->ring_calls - n + i;
+        cudaEvent_t* e = idx->ring + 4 * (call % kTimingSlots);
+        float a = 0.f, b = 0.f;
+        if (cudaEventElapsedTime(&a, e[1], e[2]) != cudaSuccess) a = -1.f;
+        if (cudaEventElapsedTime(&b, e[0], e[3]) != cudaSuccess) b = -1.f;
+        cudaGetLastError();
+        if (dominant_ms) dominant_ms[i] = a;
+        if (total_ms) total_ms[i] = b;
+    }
+    return n;
+}
+
+B2S_API int b2s_merge_packed_device(int device, const void* packed, int g, int64_t nq, int k, float* out_scores,
+                                    int64_t* out_ids, void* cuda_stream) {
+    if (!packed) return fail(B2S_ERR_INVALID, "null buffer");
+    // per rank: [ids int64 nq*k][scores fp32 nq*k], padded to a multiple of 16 bytes
+    const size_t per_rank = b2s_packed_bytes(nq, k);
+    if (g < 1 || nq < 0 || k < 0) return fail(B2S_ERR_INVALID, "bad arguments");
+    if (nq == 0 || k == 0) return B2S_OK;
+    if (!out_scores || !out_ids) return fail(B2S_ERR_INVALID, "null buffer");
+    if ((int64_t)g * k > kMergeSortCap)
+        return fail(B2S_ERR_UNSUPPORTED, "g * k exceeds the merge buffer (4096 candidates per query)");
+    CUDA_TRY(cudaSetDevice(device));
+    MergeParams mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.k = k;
+    mp.in_ids = reinterpret_cast<const long long*>(packed);
+    mp.in_scores = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(packed) + (size_t)nq * k * 8);
+    mp.g = g;
+    mp.k_in = k;
+    mp.nq = nq;
+    mp.g_stride_ids = (long long)(per_rank / 8);
+    mp.g_stride_scores = (long long)(per_rank / 4);
+    mp.out_scores = out_scores;
+    mp.out_ids = reinterpret_cast<long long*>(out_ids);
+    merge_pairs_kernel<<<(unsigned)nq, kMergeThreads, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(mp);
+    CUDA_TRY(cudaGetLastError());
+    return B2S_OK;
+}
+
+B2S_API int64_t b2s_packed_bytes(int64_t nq, int k) {
+    const int64_t raw = nq * (int64_t)k * 12;
+    return (raw + 15) / 16 * 16;
 }
 
 B2S_API const void* b2s_rows_device(const b2s_index* idx) { return idx ? idx->rows : nullptr; }

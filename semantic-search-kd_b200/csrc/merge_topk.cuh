@@ -38,6 +38,8 @@ struct MergeParams {
     int g;
     int k_in;
     long long nq;
+    long long g_stride_scores;  // elements between consecutive ranks' score blocks
+    long long g_stride_ids;     // elements between consecutive ranks' id blocks
 };
 
 __device__ __forceinline__ int next_pow2(int v) {
@@ -185,9 +187,9 @@ __global__ void __launch_bounds__(kMergeThreads) merge_pairs_kernel(const MergeP
     const int total = p.g * p.k_in;  // host guarantees total <= kMergeSortCap
     for (int i = tid; i < total; i += kMergeThreads) {
         const int g = i / p.k_in, j = i - g * p.k_in;
-        const size_t src = ((size_t)g * p.nq + q) * p.k_in + j;
-        const long long id = p.in_ids[src];
-        buf[i] = id < 0 ? 0ull : make_key(p.in_scores[src], (uint32_t)i);
+        const size_t off = (size_t)q * p.k_in + j;
+        const long long id = p.in_ids[(size_t)g * p.g_stride_ids + off];
+        buf[i] = id < 0 ? 0ull : make_key(p.in_scores[(size_t)g * p.g_stride_scores + off], (uint32_t)i);
     }
     __syncthreads();
     block_sort_desc(buf, total > 0 ? total : 1, tid);
@@ -197,9 +199,9 @@ __global__ void __launch_bounds__(kMergeThreads) merge_pairs_kernel(const MergeP
         if (i < total && buf[i] != 0ull) {
             const int pos = (int)key_row(buf[i]);
             const int g = pos / p.k_in, j = pos - g * p.k_in;
-            const size_t src = ((size_t)g * p.nq + q) * p.k_in + j;
-            s = p.in_scores[src];
-            id = p.in_ids[src];
+            const size_t off = (size_t)q * p.k_in + j;
+            s = p.in_scores[(size_t)g * p.g_stride_scores + off];
+            id = p.in_ids[(size_t)g * p.g_stride_ids + off];
         }
         p.out_scores[(size_t)q * p.k + i] = s;
         p.out_ids[(size_t)q * p.k + i] = id;

@@ -64,7 +64,11 @@ __global__ void __launch_bounds__(kScanThreads, (NQ <= 2 ? 2 : 1))
 scan_topk_kernel(const ScanParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* entries = reinterpret_cast<u64*>(smem_raw);  // [NQ][cap]
-    __shared__ ListState lists[NQ];
+    __shared__ u64 s_thr_key[NQ];
+    __shared__ float s_thr[NQ];
+    __shared__ int s_count[NQ];
+    __shared__ int s_lock[NQ];
+    auto list_of = [&](int q) { return ListRef{&s_thr_key[q], &s_thr[q], &s_count[q], &s_lock[q]}; };
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -77,11 +81,8 @@ scan_topk_kernel(const ScanParams p) {
     if (tid < NQ) {
         u64 seed = 0ull;
         if (p.seed_keys != nullptr && tid < p.nq_valid) seed = p.seed_keys[p.q_begin + tid];
-        list_init(&lists[tid], seed);
-        if (tid >= p.nq_valid) {  // masked query slot: nothing can pass
-            lists[tid].thr_key = ~0ull;
-            lists[tid].thr = INFINITY;
-        }
+        if (tid < p.nq_valid) list_init(list_of(tid), seed);
+        else list_disable(list_of(tid));  // masked query slot: nothing can pass
     }
 
     // query -> registers (fp32): lane hl keeps elements [(hl + 16 j) * 8, +8) for j < CPL
@@ -146,14 +147,14 @@ scan_topk_kernel(const ScanParams p) {
 #pragma unroll
             for (int i = 1; i < U; ++i) s = (hl == i) ? acc[q][i] : s;
             mys[q] = s;
-            pass[q] = row_ok && (s >= *(volatile float*)&lists[q].thr);
+            pass[q] = row_ok && (s >= *(volatile float*)&s_thr[q]);
             any = any || pass[q];
         }
         if (__any_sync(0xffffffffu, any)) {
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 if (__any_sync(0xffffffffu, pass[q])) {
-                    list_append_warp(&lists[q], entries + (size_t)q * p.cap, p.cap, p.k, pass[q],
+                    list_append_warp(list_of(q), entries + (size_t)q * p.cap, p.cap, p.k, pass[q],
                                      make_key(mys[q], (uint32_t)myrow), lane);
                 }
             }
@@ -163,12 +164,12 @@ scan_topk_kernel(const ScanParams p) {
 
     // final: leave exactly min(count, k) best keys per query, then publish
     for (int q = warp; q < NQ; q += kScanWarps) {
-        if (*(volatile int*)&lists[q].count > p.k)
-            list_compact_warp(&lists[q], entries + (size_t)q * p.cap, p.cap, p.k, lane);
+        if (*(volatile int*)&s_count[q] > p.k)
+            list_compact_warp(list_of(q), entries + (size_t)q * p.cap, p.cap, p.k, lane);
     }
     __syncthreads();
     for (int q = 0; q < p.nq_valid; ++q) {
-        const int c = lists[q].count;
+        const int c = s_count[q];
         u64* dst = p.lists + ((size_t)blockIdx.x * p.nq_lists + (p.q_begin + q)) * p.cap;
         for (int i = tid; i < c; i += kScanThreads) dst[i] = entries[(size_t)q * p.cap + i];
         if (tid == 0) p.counts[(size_t)blockIdx.x * p.nq_lists + (p.q_begin + q)] = c;

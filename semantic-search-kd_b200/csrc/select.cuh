@@ -72,73 +72,100 @@ struct BlockSync {
     __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
 
-// Per-(CTA, query) list state kept in shared memory.
-struct ListState {
-    u64 thr_key;   // a candidate must have key > thr_key
-    float thr;     // fast test: score >= thr   (score of thr_key, -inf when unset)
-    int count;     // entries currently in the list
-    int lock;      // 0 free, 1 held
-    int pad;
+// Per-(CTA, query) list state, kept in shared memory.  Held as separate arrays by the kernels
+// (the tensor-core epilogue reads thresholds as broadcast vectors), referenced through ListRef.
+struct ListRef {
+    u64* thr_key;   // a candidate must have key > *thr_key
+    float* thr;     // fast test: score >= *thr  (score of thr_key, -inf when unset)
+    int* count;     // entries currently in the list
+    int* lock;      // 0 free, 1 held
 };
 
-__device__ __forceinline__ void list_init(ListState* st, u64 seed_key) {
-    st->thr_key = seed_key;
-    st->thr = seed_key ? key_score(seed_key) : -INFINITY;
-    st->count = 0;
-    st->lock = 0;
-    st->pad = 0;
+__device__ __forceinline__ void list_init(const ListRef& st, u64 seed_key) {
+    *st.thr_key = seed_key;
+    *st.thr = seed_key ? key_score(seed_key) : -INFINITY;
+    *st.count = 0;
+    *st.lock = 0;
+}
+__device__ __forceinline__ void list_disable(const ListRef& st) {  // masked query slot
+    *st.thr_key = ~0ull;
+    *st.thr = INFINITY;
+    *st.count = 0;
+    *st.lock = 0;
 }
 
-// One warp sorts entries[0..cap) (entries beyond count are zeroed first), keeps the best k and
-// publishes the new threshold.  Caller holds the lock.  Returns the new count.
-__device__ __forceinline__ int list_compact_warp(ListState* st, u64* entries, int cap, int k, int lane) {
-    int c = *(volatile int*)&st->count;
-    for (int i = c + lane; i < cap; i += 32) entries[i] = 0ull;
-    __syncwarp();
-    bitonic_sort_desc(entries, cap, lane, 32, WarpSync());
-    int keep = c < k ? c : k;
+__device__ __forceinline__ void spin_acquire(int* lock, int lane) {
     if (lane == 0) {
-        if (c >= k) {
-            u64 kth = entries[k - 1];
-            *(volatile u64*)&st->thr_key = kth;
-            *(volatile float*)&st->thr = key_score(kth);
-        }
-        *(volatile int*)&st->count = keep;
+        while (atomicCAS(lock, 0, 1) != 0) __nanosleep(32);
     }
     __syncwarp();
+    __threadfence_block();
+}
+__device__ __forceinline__ void spin_release(int* lock, int lane) {
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) atomicExch(lock, 0);
+    __syncwarp();
+}
+
+// One warp keeps the best k of entries[0..count) and publishes the new threshold.  The sort runs
+// in `work` (shared memory, >= cap slots): for a shared-memory list work == entries; for a
+// global-memory list the keys are staged through the CTA's scratch buffer (scratch_lock).
+// Caller holds the list lock.  Returns the new count.
+__device__ __forceinline__ int list_compact_warp(const ListRef& st, u64* entries, int cap, int k, int lane,
+                                                 u64* scratch = nullptr, int* scratch_lock = nullptr) {
+    const int c = *(volatile int*)st.count;
+    u64* work = entries;
+    if (scratch != nullptr) {
+        spin_acquire(scratch_lock, lane);
+        for (int i = lane; i < c; i += 32) scratch[i] = entries[i];
+        work = scratch;
+    }
+    for (int i = c + lane; i < cap; i += 32) work[i] = 0ull;
+    __syncwarp();
+    bitonic_sort_desc(work, cap, lane, 32, WarpSync());
+    const int keep = c < k ? c : k;
+    if (scratch != nullptr) {
+        for (int i = lane; i < keep; i += 32) entries[i] = work[i];
+    }
+    __syncwarp();
+    if (lane == 0) {
+        if (c >= k) {
+            const u64 kth = work[k - 1];
+            *(volatile u64*)st.thr_key = kth;
+            *(volatile float*)st.thr = key_score(kth);
+        }
+        *(volatile int*)st.count = keep;
+    }
+    __syncwarp();
+    if (scratch != nullptr) spin_release(scratch_lock, lane);
     return keep;
 }
 
 // Warp-collective append.  Every lane of the warp calls it (converged); `pass` says whether this
-// lane offers `key`.  entries has `cap` slots (shared or global memory).
-__device__ __forceinline__ void list_append_warp(ListState* st, u64* entries, int cap, int k, bool pass,
-                                                 u64 key, int lane) {
-    if (lane == 0) {
-        while (atomicCAS(&st->lock, 0, 1) != 0) __nanosleep(32);
-    }
-    __syncwarp();
-    __threadfence_block();
-    u64 tk = *(volatile u64*)&st->thr_key;
+// lane offers `key`.  entries has `cap` slots (shared memory, or global memory with a scratch).
+__device__ __forceinline__ void list_append_warp(const ListRef& st, u64* entries, int cap, int k, bool pass,
+                                                 u64 key, int lane, u64* scratch = nullptr,
+                                                 int* scratch_lock = nullptr) {
+    spin_acquire(st.lock, lane);
+    u64 tk = *(volatile u64*)st.thr_key;
     pass = pass && (key > tk);
     unsigned m = __ballot_sync(0xffffffffu, pass);
     int n = __popc(m);
     if (n) {
-        int c = *(volatile int*)&st->count;
+        int c = *(volatile int*)st.count;
         if (c + n > cap) {
-            c = list_compact_warp(st, entries, cap, k, lane);
-            tk = *(volatile u64*)&st->thr_key;
+            c = list_compact_warp(st, entries, cap, k, lane, scratch, scratch_lock);
+            tk = *(volatile u64*)st.thr_key;
             pass = pass && (key > tk);
             m = __ballot_sync(0xffffffffu, pass);
             n = __popc(m);
         }
         if (pass) entries[c + __popc(m & ((1u << lane) - 1u))] = key;
         __syncwarp();
-        if (lane == 0) *(volatile int*)&st->count = c + n;
+        if (lane == 0) *(volatile int*)st.count = c + n;
     }
-    __threadfence_block();
-    __syncwarp();
-    if (lane == 0) atomicExch(&st->lock, 0);
-    __syncwarp();
+    spin_release(st.lock, lane);
 }
 
 }  // namespace b2s

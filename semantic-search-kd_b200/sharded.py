@@ -1,0 +1,140 @@
+"""Row-sharded exact search across the GPUs of one box.
+
+One process per GPU (``torch.distributed``, backend ``nccl``).  Rank r holds the contiguous row
+range ``[r*ceil(N/G), min(N, (r+1)*ceil(N/G)))``; global id = range start + local row, so the
+``doc_ids[idx]`` mapping of ``/root/reference/src/serve/app.py:303`` is unchanged.  Queries are
+replicated (``dim*4`` bytes each).  A search is
+
+    local top-k on every rank (K1/K2 + K3, ids already global)
+      -> ONE all-gather of the packed candidate block (k*12 bytes per query per rank) over NVLink
+      -> K4 merge of G*k candidates per query on every rank (ties -> lower id).
+
+The reference has no multi-device path; this realises the "shard across
+instances, fan out, merge" prose of ``docs/operations/scaling-and-performance.md:154-172``.
+
+``local_index`` / ``merge_fn`` are injectable so that the plumbing (ranges, gather order, packing)
+is testable with the ``gloo`` backend on CPU; the defaults are the CUDA implementations and there
+is no CPU fallback in the product path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from .errors import IndexBuildError, IndexNotBuiltError
+from .index import FlatIPIndex, _check
+
+try:
+    import torch
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    torch = None  # type: ignore
+    dist = None  # type: ignore
+
+
+def shard_range(n_total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row range of ``rank`` (empty ranges allowed when ``n_total < world``)."""
+    per = -(-n_total // world) if n_total > 0 else 0
+    lo = min(n_total, rank * per)
+    hi = min(n_total, lo + per)
+    return lo, hi
+
+
+def packed_bytes(nq: int, k: int) -> int:
+    """Bytes of one rank's packed candidate block: [ids int64 nq*k][scores fp32 nq*k], 16-aligned."""
+    return (nq * k * 12 + 15) // 16 * 16
+
+
+class ShardedFlatIPIndex:
+    """Exact top-k over a corpus row-sharded across the ranks of a process group."""
+
+    def __init__(self, embedding_dim: int = 384, metric: str = "cosine", group=None,
+                 local_index: Optional[FlatIPIndex] = None,
+                 merge_fn: Optional[Callable] = None, device: Optional[int] = None) -> None:
+        if dist is None or not dist.is_initialized():
+            raise IndexBuildError("torch.distributed must be initialised before ShardedFlatIPIndex")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.embedding_dim = int(embedding_dim)
+        self.local = local_index if local_index is not None else FlatIPIndex(embedding_dim, metric=metric,
+                                                                              device=device)
+        self._merge_fn = merge_fn
+        self.n_total = 0
+        self.range = (0, 0)
+        self._bufs = {}
+
+    # ------------------------------------------------------------------ build
+    def build_from_embeddings(self, embeddings, n_total: Optional[int] = None) -> "ShardedFlatIPIndex":
+        """Every rank passes the FULL array (or only needs its slice to be valid); each keeps its range."""
+        n = int(n_total if n_total is not None else embeddings.shape[0])
+        lo, hi = shard_range(n, self.world, self.rank)
+        self.local.build_from_embeddings(embeddings[lo:hi])
+        self.local.set_id_offset(lo)
+        self.n_total, self.range = n, (lo, hi)
+        return self
+
+    def add_local(self, local_rows, n_total: int) -> "ShardedFlatIPIndex":
+        """Append this rank's own rows (generated or loaded shard-locally); ``n_total`` = global rows."""
+        lo, hi = shard_range(int(n_total), self.world, self.rank)
+        self.local.add(local_rows)
+        if self.local.ntotal > hi - lo:
+            raise IndexBuildError(f"rank {self.rank} holds {self.local.ntotal} rows, its range has {hi - lo}")
+        self.local.set_id_offset(lo)
+        self.n_total, self.range = int(n_total), (lo, hi)
+        return self
+
+    @property
+    def ntotal(self) -> int:
+        return self.n_total
+
+    # ------------------------------------------------------------------ search
+    def _buffers(self, nq: int, k: int, device):
+        key = (nq, k, str(device))
+        b = self._bufs.get(key)
+        if b is None:
+            per = packed_bytes(nq, k)
+            gathered = torch.empty((self.world, per), dtype=torch.uint8, device=device)
+            mine = gathered[self.rank]
+            ids = mine[: nq * k * 8].view(torch.int64).view(nq, k)
+            scores = mine[nq * k * 8: nq * k * 12].view(torch.float32).view(nq, k)
+            out_s = torch.empty((nq, k), dtype=torch.float32, device=device)
+            out_i = torch.empty((nq, k), dtype=torch.int64, device=device)
+            b = (gathered, mine, scores, ids, out_s, out_i)
+            self._bufs = {key: b}  # keep only the latest shape
+        return b
+
+    def search_device(self, q: "torch.Tensor", k: int):
+        """Device-resident sharded search on the current stream; returns CUDA tensors (all ranks)."""
+        if self.n_total == 0 and self.local.ntotal == 0 and self.local._h is None:
+            raise IndexNotBuiltError()
+        nq = q.shape[0]
+        gathered, mine, scores, ids, out_s, out_i = self._buffers(nq, k, q.device)
+        self.local.search_device(q, k, out=(scores, ids))
+        if self.world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), mine, group=self.group)
+        if self._merge_fn is not None:
+            self._merge_fn(gathered, self.world, nq, k, out_s, out_i)
+        else:
+            stream = torch.cuda.current_stream(q.device).cuda_stream
+            _check(_lib.lib().b2s_merge_packed_device(q.device.index, ctypes.c_void_p(gathered.data_ptr()),
+                                                      self.world, nq, int(k), ctypes.c_void_p(out_s.data_ptr()),
+                                                      ctypes.c_void_p(out_i.data_ptr()), ctypes.c_void_p(stream)),
+                   "b2s_merge_packed_device")
+        return out_s, out_i
+
+    def search(self, query_emb, k: int = 10):
+        """``search(query_emb, k) -> (scores, ids)``: numpy in -> numpy out (H2D / D2H inside),
+        CUDA tensor in -> CUDA tensors out.  Every rank must call it with the same queries."""
+        if torch is not None and isinstance(query_emb, torch.Tensor) and query_emb.is_cuda:
+            return self.search_device(query_emb, k)
+        q = np.ascontiguousarray(np.asarray(query_emb, dtype=np.float32))
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        dev = torch.device("cuda", self.local.device if self.local.device is not None else torch.cuda.current_device())
+        qd = torch.from_numpy(q).to(dev, non_blocking=False)
+        s, i = self.search_device(qd, k)
+        return s.cpu().numpy(), i.cpu().numpy()

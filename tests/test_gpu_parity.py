@@ -1,0 +1,274 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bar (BASELINE.json north_star): ids identical to the fp32 flat oracle, swaps allowed only between
+ties whose fp32 scores agree within 1e-3 under bf16 storage.  Tighter checks where available:
+against the oracle run on the SAME bf16-rounded corpus the device holds, the scan path (fp32
+query, fp32 accumulate) must agree to fp32 summation-order noise (1e-5).
+"""
+import numpy as np
+import pytest
+
+from conftest import unit_rows
+
+pytestmark = pytest.mark.gpu
+
+TIE_TOL_BF16 = 1e-3     # north_star tolerance for bf16 storage
+TIE_TOL_F32 = 2e-5      # fp32 summation-order noise
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    import semantic_search_kd_b200 as m
+    return m
+
+
+def build(pkg, X, metric="inner_product", **opts):
+    idx = pkg.FlatIPIndex(X.shape[1], metric=metric)
+    for k, v in opts.items():
+        idx.set_option(k, v)
+    idx.add(X)
+    return idx
+
+
+def check(oracle, idx, X, Q, k, tight=True):
+    D, I = idx.search(Q, k)
+    assert D.shape == (Q.shape[0], k) and I.shape == (Q.shape[0], k)
+    assert D.dtype == np.float32 and I.dtype == np.int64
+    Dr, Ir = oracle.flat_ip_topk(X, Q, k)
+    rep = oracle.compare_topk(D, I, Dr, Ir, X, Q, tie_tol=TIE_TOL_BF16)
+    assert rep["ok"], rep
+    assert rep["max_abs_score_err"] <= TIE_TOL_BF16, rep
+    valid = I >= 0
+    assert np.all(np.diff(np.where(valid, D, -np.inf), axis=1)[valid[:, 1:]] <= 0), "scores not descending"
+    if tight:
+        Xb = oracle.round_bf16(X)
+        Db, Ib = oracle.flat_ip_topk(Xb, Q, k)
+        rep2 = oracle.compare_topk(D, I, Db, Ib, Xb, Q, tie_tol=TIE_TOL_F32)
+        assert rep2["ok"], rep2
+        assert rep2["max_abs_score_err"] <= TIE_TOL_F32, rep2
+    return D, I
+
+
+def test_golden_vectors_scan_path(pkg, oracle, golden_cases):
+    for name, (X, Q, z) in golden_cases.items():
+        idx = build(pkg, X, path=1)
+        for k in sorted(int(f[5:]) for f in z.files if f.startswith("ids_k")):
+            D, I = idx.search(Q, k)
+            ref_I, ref_D = z[f"ids_k{k}"], z[f"scores_k{k}"]
+            rep = oracle.compare_topk(D, I, ref_D, ref_I, X, Q, tie_tol=TIE_TOL_BF16)
+            assert rep["ok"], (name, k, rep)
+            if f"ids_bf16corpus_k{k}" in z.files:   # same rounding as the device: must be identical
+                rep = oracle.compare_topk(D, I, z[f"scores_bf16corpus_k{k}"], z[f"ids_bf16corpus_k{k}"],
+                                          oracle.round_bf16(X), Q, tie_tol=TIE_TOL_F32)
+                assert rep["ok"], (name, k, rep)
+                if name == "rand2000":
+                    assert np.array_equal(I, z[f"ids_bf16corpus_k{k}"]), (name, k)
+        idx.close()
+
+
+def test_conftest_fixture_identity(pkg, golden_cases):
+    """The reference fixture (tests/conftest.py:65-73): query = corpus row -> top-1 is itself, score 1."""
+    X, Q, z = golden_cases["conftest_fixture"]
+    idx = build(pkg, X)
+    D, I = idx.search(X, 1)
+    assert list(I[:, 0]) == list(range(10))
+    np.testing.assert_allclose(D[:, 0], 1.0, atol=4e-3)
+    D, I = idx.search(Q, 12)                       # k > ntotal
+    assert np.all(I[:, 10:] == -1) and np.all(D[:, 10:] == np.float32(-3.4028234663852886e38))
+    assert np.array_equal(np.sort(I[:, :10], axis=1), np.tile(np.arange(10), (Q.shape[0], 1)))
+    idx.close()
+
+
+@pytest.mark.parametrize("n", [1, 7, 63, 64, 65, 1000, 4097, 50000])
+@pytest.mark.parametrize("nq", [1, 2, 3, 4, 7])
+def test_ragged_sizes_scan(pkg, oracle, n, nq):
+    X, Q = unit_rows(n, 384, n), unit_rows(nq, 384, 1000 + nq)
+    idx = build(pkg, X, path=1)
+    for k in (1, 10):
+        check(oracle, idx, X, Q, k)
+    idx.close()
+
+
+@pytest.mark.parametrize("k", [1, 10, 32, 100, 200, 1000, 2048])
+def test_k_sweep_scan(pkg, oracle, k):
+    X, Q = unit_rows(30000, 384, 5), unit_rows(3, 384, 6)
+    for seed in (0, 1):
+        idx = build(pkg, X, path=1, seed=seed)
+        check(oracle, idx, X, Q, k)
+        assert idx.stats()["seeded"] == seed
+        idx.close()
+
+
+def test_exact_ties_prefer_lower_id(pkg, oracle):
+    X = unit_rows(5000, 384, 9)
+    X[100:140] = X[7]            # 41 identical rows -> identical scores
+    X[4990:] = X[7]
+    Q = np.concatenate([X[[7]], unit_rows(2, 384, 10)])
+    idx = build(pkg, X, path=1)
+    D, I = idx.search(Q, 20)
+    assert list(I[0]) == [7] + list(range(100, 119)), I[0]
+    check(oracle, idx, X, Q, 20)
+    idx.close()
+
+
+def test_adversarial_ascending_scores(pkg, oracle):
+    """Every row beats all earlier ones: the candidate lists overflow and compact continuously."""
+    rng = np.random.default_rng(3)
+    q = unit_rows(1, 384, 77)[0]
+    noise = unit_rows(20000, 384, 78)
+    t = np.linspace(-0.9, 0.9, 20000, dtype=np.float32)[:, None]
+    X = t * q[None, :] + 0.05 * noise
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    X = X.astype(np.float32)
+    Q = np.stack([q, -q]).astype(np.float32)
+    idx = build(pkg, X, path=1)
+    for k in (10, 100):
+        check(oracle, idx, X, Q, k)
+    idx.close()
+
+
+def test_all_equal_scores(pkg):
+    X = np.tile(unit_rows(1, 384, 1), (3000, 1))
+    idx = build(pkg, X, path=1)
+    D, I = idx.search(X[:1], 50)
+    assert list(I[0]) == list(range(50))
+    idx.close()
+
+
+def test_cosine_metric_normalises(pkg, oracle):
+    rng = np.random.default_rng(4)
+    Xr = rng.standard_normal((4000, 384)).astype(np.float32) * rng.uniform(0.1, 9, (4000, 1)).astype(np.float32)
+    Qr = rng.standard_normal((5, 384)).astype(np.float32) * 3
+    X = Xr / np.linalg.norm(Xr, axis=1, keepdims=True)
+    Q = Qr / np.linalg.norm(Qr, axis=1, keepdims=True)
+    idx = build(pkg, Xr, metric="cosine", path=1)
+    D, I = idx.search(Qr, 10)
+    Dr, Ir = oracle.flat_ip_topk(X, Q, 10)
+    rep = oracle.compare_topk(D, I, Dr, Ir, X, Q, tie_tol=TIE_TOL_BF16)
+    assert rep["ok"], rep
+    idx.close()
+
+
+def test_incremental_add_and_id_offset(pkg, oracle):
+    X, Q = unit_rows(9000, 384, 31), unit_rows(4, 384, 32)
+    idx = pkg.FlatIPIndex(384, metric="inner_product")
+    for s in range(0, 9000, 2500):
+        idx.add(X[s:s + 2500])
+    assert idx.ntotal == 9000
+    check(oracle, idx, X, Q, 10)
+    idx.set_id_offset(1_000_000_000_000)
+    D, I = idx.search(Q, 10)
+    Dr, Ir = oracle.flat_ip_topk(oracle.round_bf16(X), Q, 10)
+    assert np.array_equal(I - 1_000_000_000_000, Ir)
+    idx.close()
+
+
+def test_torch_device_path_and_bf16_queries(pkg, oracle):
+    import torch
+    X, Q = unit_rows(20000, 384, 41), unit_rows(6, 384, 42)
+    idx = pkg.FlatIPIndex(384, metric="inner_product")
+    idx.set_option("path", 1)
+    idx.add(torch.from_numpy(X).cuda())
+    s, i = idx.search(torch.from_numpy(Q).cuda(), 10)
+    assert s.is_cuda and i.is_cuda and s.dtype == torch.float32 and i.dtype == torch.int64
+    Dr, Ir = oracle.flat_ip_topk(X, Q, 10)
+    rep = oracle.compare_topk(s.cpu().numpy(), i.cpu().numpy(), Dr, Ir, X, Q, tie_tol=TIE_TOL_BF16)
+    assert rep["ok"], rep
+    s2, i2 = idx.search(torch.from_numpy(Q).cuda().bfloat16(), 10)
+    Qb = oracle.round_bf16(Q)
+    Db, Ib = oracle.flat_ip_topk(oracle.round_bf16(X), Qb, 10)
+    rep = oracle.compare_topk(s2.cpu().numpy(), i2.cpu().numpy(), Db, Ib, oracle.round_bf16(X), Qb,
+                              tie_tol=TIE_TOL_F32)
+    assert rep["ok"], rep
+    idx.close()
+
+
+def test_empty_index_and_zero_k(pkg):
+    idx = pkg.FlatIPIndex(384, metric="inner_product")
+    idx.add(np.zeros((0, 384), np.float32))
+    D, I = idx.search(unit_rows(2, 384, 1), 5)
+    assert np.all(I == -1)
+    D, I = idx.search(unit_rows(2, 384, 1), 0)
+    assert D.shape == (2, 0)
+    D, I = idx.search(np.zeros((0, 384), np.float32), 5)
+    assert D.shape == (0, 5)
+    idx.close()
+
+
+def test_other_dims(pkg, oracle):
+    for d in (128, 256, 512, 768, 1024):
+        X, Q = unit_rows(3000, d, d), unit_rows(3, d, d + 1)
+        idx = build(pkg, X, path=1)
+        D, I = idx.search(Q, 10)
+        Dr, Ir = oracle.flat_ip_topk(oracle.round_bf16(X), Q, 10)
+        rep = oracle.compare_topk(D, I, Dr, Ir, oracle.round_bf16(X), Q, tie_tol=TIE_TOL_F32)
+        assert rep["ok"], (d, rep)
+        idx.close()
+
+
+def test_save_load_roundtrip(pkg, oracle, tmp_path):
+    X, Q = unit_rows(3000, 384, 51), unit_rows(3, 384, 52)
+    idx = build(pkg, X)
+    idx.doc_ids = [f"doc_{i}" for i in range(3000)]
+    D0, I0 = idx.search(Q, 10)
+    idx.save(tmp_path / "index")
+    assert (tmp_path / "index" / "index.faiss").stat().st_size == 45 + 3000 * 384 * 4
+    for drop_sidecar in (False, True):
+        if drop_sidecar:
+            (tmp_path / "index" / "rows.bf16").unlink()
+        j = pkg.FAISSIndexBuilder(embedding_dim=384, metric="inner_product")
+        j.load(tmp_path / "index")          # src/serve/app.py:430-433
+        assert j.ntotal == 3000 and j.doc_ids[5] == "doc_5"
+        D1, I1 = j.search(Q, 10)
+        assert np.array_equal(I0, I1) and np.array_equal(D0, D1)
+        j.close()
+    idx.close()
+
+
+def test_similarity_matches_oracle(pkg, oracle):
+    """compute_similarity (tests/test_student_model.py:104-124): shape (2,3), range, values."""
+    import ctypes
+    L = pkg._lib.lib()
+    q, d = unit_rows(2, 384, 1), unit_rows(3, 384, 2)
+    out = np.empty((2, 3), np.float32)
+    rc = L.b2s_similarity(0, q.ctypes.data_as(ctypes.c_void_p), 2, d.ctypes.data_as(ctypes.c_void_p), 3, 384,
+                          out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0, pkg._lib.last_error()
+    assert out.shape == (2, 3) and np.all(out >= -1.01) and np.all(out <= 1.01)
+    np.testing.assert_allclose(out, oracle.similarity_np(q, d), atol=1e-6)
+
+
+def test_merge_device_matches_global_topk(pkg, oracle):
+    """Row-sharded search emulated on one GPU: G shards searched one after another, candidates
+    stacked as the all-gather would, merged by b2s_merge_device."""
+    import ctypes
+    import torch
+    X, Q = unit_rows(40000, 384, 61), unit_rows(5, 384, 62)
+    X[30000:30010] = X[5]     # ties across shards
+    Q[0] = X[5]
+    G, k = 4, 10
+    parts = np.array_split(np.arange(40000), G)
+    sc, ids = [], []
+    for p in parts:
+        idx = build(pkg, X[p], path=1)
+        idx.set_id_offset(int(p[0]))
+        s, i = idx.search(torch.from_numpy(Q).cuda(), k)
+        sc.append(s)
+        ids.append(i)
+        idx.close()
+    S = torch.stack(sc).contiguous()
+    I = torch.stack(ids).contiguous()
+    outS = torch.empty((5, k), dtype=torch.float32, device="cuda")
+    outI = torch.empty((5, k), dtype=torch.int64, device="cuda")
+    rc = pkg._lib.lib().b2s_merge_device(0, ctypes.c_void_p(S.data_ptr()), ctypes.c_void_p(I.data_ptr()), G, 5, k,
+                                         ctypes.c_void_p(outS.data_ptr()), ctypes.c_void_p(outI.data_ptr()),
+                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, pkg._lib.last_error()
+    torch.cuda.synchronize()
+    Xb = oracle.round_bf16(X)
+    Dr, Ir = oracle.flat_ip_topk(Xb, Q, k)
+    rep = oracle.compare_topk(outS.cpu().numpy(), outI.cpu().numpy(), Dr, Ir, Xb, Q, tie_tol=TIE_TOL_F32)
+    assert rep["ok"], rep
+    assert list(outI[0].cpu().numpy()[:3]) == [5, 30000, 30001]
