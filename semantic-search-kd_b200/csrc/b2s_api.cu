@@ -279,6 +279,12 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
     return B2S_OK;
 }
 
+#ifndef B2S_NO_TENSOR_PATH
+int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, int k, float* out_scores,
+                  int64_t* out_ids, cudaStream_t s, bool seed, bool normalize);
+void tensor_path_release(b2s_index* idx);
+#endif
+
 int search_impl(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, int k, float* out_scores,
                 int64_t* out_ids, cudaStream_t s) {
     if (!idx) return fail(B2S_ERR_INVALID, "null index");

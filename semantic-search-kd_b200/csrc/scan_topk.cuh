@@ -106,18 +106,37 @@ scan_topk_kernel(const ScanParams p) {
     if (row_end > p.n_rows) row_end = p.n_rows;
     const long long last_row = p.n_rows - 1;
 
+    // Rare path, kept out of line of the hot loop: pick the row this lane speaks for (lane hl < U
+    // of each half-warp owns row base + 2*hl + half), re-test it and append under the list lock.
+    auto offer = [&](long long base, const float (&acc)[NQ][U]) {
+        const long long myrow = base + 2 * hl + half;
+        const bool row_ok = (hl < U) && (myrow < row_end);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            float s = acc[q][0];
+#pragma unroll
+            for (int i = 1; i < U; ++i) s = (hl == i) ? acc[q][i] : s;
+            const bool pass = row_ok && (s >= *(volatile float*)&s_thr[q]);
+            if (__any_sync(0xffffffffu, pass)) {
+                list_append_warp(list_of(q), entries + (size_t)q * p.cap, p.cap, p.k, pass,
+                                 make_key(s, (uint32_t)myrow), lane);
+            }
+        }
+    };
+
     const long long step = (long long)kScanWarps * kRowsPerIter * p.unit_stride;
-    for (long long base = row_begin + (long long)warp * kRowsPerIter * p.unit_stride; base < row_end;
-         base += step) {
+    long long base = row_begin + (long long)warp * kRowsPerIter * p.unit_stride;
+    // lane's pointer to chunk hl of row (base + half); advanced by `step` rows per iteration
+    const uint4* rp = p.corpus + (base + half) * kChunksPerRow + hl;
+    const long long rp_step = step * kChunksPerRow;
+
+    // ---- hot loop: all 2U rows of the unit exist; no clamps, no per-lane selects ----------------
+    for (; base + kRowsPerIter <= row_end; base += step, rp += rp_step) {
         uint4 w[U][CPL];
 #pragma unroll
-        for (int i = 0; i < U; ++i) {
-            long long r = base + 2 * i + half;
-            if (r > last_row) r = last_row;  // clamp: loads stay in bounds, masked below
-            const uint4* rp = p.corpus + r * kChunksPerRow + hl;
+        for (int i = 0; i < U; ++i)
 #pragma unroll
-            for (int j = 0; j < CPL; ++j) w[i][j] = ldg_stream(rp + 16 * j);
-        }
+            for (int j = 0; j < CPL; ++j) w[i][j] = ldg_stream(rp + (2 * i) * kChunksPerRow + 16 * j);
         float acc[NQ][U];
 #pragma unroll
         for (int q = 0; q < NQ; ++q)
@@ -134,31 +153,45 @@ scan_topk_kernel(const ScanParams p) {
             for (int q = 0; q < NQ; ++q)
 #pragma unroll
                 for (int i = 0; i < U; ++i) acc[q][i] += __shfl_xor_sync(0xffffffffu, acc[q][i], off);
-
-        // lane hl (< U) of each half-warp speaks for row base + 2*hl + half
-        const long long myrow = base + 2 * hl + half;
-        const bool row_ok = (hl < U) && (myrow < row_end);
-        bool any = false;
-        float mys[NQ];
-        bool pass[NQ];
+        // after the butterfly every lane of a half-warp holds all U sums of its half
+        bool hot = false;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-            float s = acc[q][0];
+            const float t = *(volatile float*)&s_thr[q];
 #pragma unroll
-            for (int i = 1; i < U; ++i) s = (hl == i) ? acc[q][i] : s;
-            mys[q] = s;
-            pass[q] = row_ok && (s >= *(volatile float*)&s_thr[q]);
-            any = any || pass[q];
+            for (int i = 0; i < U; ++i) hot = hot || (acc[q][i] >= t);
         }
-        if (__any_sync(0xffffffffu, any)) {
+        if (__any_sync(0xffffffffu, hot)) offer(base, acc);
+        __syncwarp();
+    }
+
+    // ---- tail: the (at most one) partial unit of this warp, loads clamped to the last row --------
+    if (base < row_end) {
+        float acc[NQ][U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+            long long r = base + 2 * i + half;
+            if (r > last_row) r = last_row;
+            const uint4* tp = p.corpus + r * kChunksPerRow + hl;
+            uint4 w[CPL];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) w[j] = ldg_stream(tp + 16 * j);
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
-                if (__any_sync(0xffffffffu, pass[q])) {
-                    list_append_warp(list_of(q), entries + (size_t)q * p.cap, p.cap, p.k, pass[q],
-                                     make_key(mys[q], (uint32_t)myrow), lane);
-                }
+                float a = 0.f;
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) a = dot8(w[j], qreg[q][j], a);
+                acc[q][i] = a;
             }
         }
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                for (int i = 0; i < U; ++i) acc[q][i] += __shfl_xor_sync(0xffffffffu, acc[q][i], off);
+        offer(base, acc);
+        __syncwarp();
     }
     __syncthreads();
 

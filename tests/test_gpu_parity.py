@@ -32,7 +32,8 @@ def build(pkg, X, metric="inner_product", **opts):
     return idx
 
 
-def check(oracle, idx, X, Q, k, tight=True):
+def check(oracle, idx, X, Q, k, tight=True, q_bf16=False):
+    """q_bf16: the tensor path rounds the queries to bf16 as well (tcgen05 operands are bf16)."""
     D, I = idx.search(Q, k)
     assert D.shape == (Q.shape[0], k) and I.shape == (Q.shape[0], k)
     assert D.dtype == np.float32 and I.dtype == np.int64
@@ -44,8 +45,9 @@ def check(oracle, idx, X, Q, k, tight=True):
     assert np.all(np.diff(np.where(valid, D, -np.inf), axis=1)[valid[:, 1:]] <= 0), "scores not descending"
     if tight:
         Xb = oracle.round_bf16(X)
-        Db, Ib = oracle.flat_ip_topk(Xb, Q, k)
-        rep2 = oracle.compare_topk(D, I, Db, Ib, Xb, Q, tie_tol=TIE_TOL_F32)
+        Qt = oracle.round_bf16(Q) if q_bf16 else Q
+        Db, Ib = oracle.flat_ip_topk(Xb, Qt, k)
+        rep2 = oracle.compare_topk(D, I, Db, Ib, Xb, Qt, tie_tol=TIE_TOL_F32)
         assert rep2["ok"], rep2
         assert rep2["max_abs_score_err"] <= TIE_TOL_F32, rep2
     return D, I
@@ -272,3 +274,84 @@ def test_merge_device_matches_global_topk(pkg, oracle):
     rep = oracle.compare_topk(outS.cpu().numpy(), outI.cpu().numpy(), Dr, Ir, Xb, Q, tie_tol=TIE_TOL_F32)
     assert rep["ok"], rep
     assert list(outI[0].cpu().numpy()[:3]) == [5, 30000, 30001]
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor path (K2: TMA + tcgen05 + TMEM epilogue), forced with path=2
+# ------------------------------------------------------------------------------------------------
+
+def test_golden_vectors_tensor_path(pkg, oracle, golden_cases):
+    for name, (X, Q, z) in golden_cases.items():
+        idx = build(pkg, X, path=2)
+        for k in sorted(int(f[5:]) for f in z.files if f.startswith("ids_k")):
+            D, I = idx.search(Q, k)
+            assert idx.stats()["path"] == 2
+            rep = oracle.compare_topk(D, I, z[f"scores_k{k}"], z[f"ids_k{k}"], X, Q, tie_tol=TIE_TOL_BF16)
+            assert rep["ok"], (name, k, rep)
+        idx.close()
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 1000, 20000])
+@pytest.mark.parametrize("nq", [1, 5, 31, 32, 33, 64, 100, 129, 300])
+def test_ragged_sizes_tensor(pkg, oracle, n, nq):
+    X, Q = unit_rows(n, 384, n + 7), unit_rows(nq, 384, 2000 + nq)
+    idx = build(pkg, X, path=2)
+    check(oracle, idx, X, Q, 10, q_bf16=True)
+    idx.close()
+
+
+@pytest.mark.parametrize("k", [1, 10, 100, 200, 1000, 2048])
+def test_k_sweep_tensor(pkg, oracle, k):
+    X, Q = unit_rows(40000, 384, 15), unit_rows(70, 384, 16)
+    for seed in (0, 1):
+        idx = build(pkg, X, path=2, seed=seed)
+        check(oracle, idx, X, Q, k, q_bf16=True)
+        idx.close()
+
+
+def test_tensor_ties_and_adversarial(pkg, oracle):
+    X = unit_rows(6000, 384, 19)
+    X[200:260] = X[9]
+    X[5990:] = X[9]
+    Q = np.concatenate([X[[9]], unit_rows(40, 384, 20)])
+    idx = build(pkg, X, path=2)
+    D, I = idx.search(Q, 20)
+    assert list(I[0]) == [9] + list(range(200, 219)), I[0]
+    check(oracle, idx, X, Q, 20, q_bf16=True)
+    idx.close()
+    # ascending scores: every tile raises every threshold
+    q = unit_rows(1, 384, 77)[0]
+    t = np.linspace(-0.9, 0.9, 30000, dtype=np.float32)[:, None]
+    Xa = t * q[None, :] + 0.05 * unit_rows(30000, 384, 78)
+    Xa = (Xa / np.linalg.norm(Xa, axis=1, keepdims=True)).astype(np.float32)
+    Qa = np.concatenate([np.stack([q, -q]), unit_rows(30, 384, 79)]).astype(np.float32)
+    idx = build(pkg, Xa, path=2)
+    for k in (10, 100):
+        check(oracle, idx, Xa, Qa, k, q_bf16=True)
+    idx.close()
+
+
+def test_scan_and_tensor_paths_agree(pkg, oracle):
+    X, Q = unit_rows(100000, 384, 91), unit_rows(16, 384, 92)
+    a = build(pkg, X, path=1)
+    b = build(pkg, X, path=2)
+    Da, Ia = a.search(Q, 10)
+    Db, Ib = b.search(Q, 10)
+    Dr, Ir = oracle.flat_ip_topk(X, Q, 10)
+    for D, I in ((Da, Ia), (Db, Ib)):
+        rep = oracle.compare_topk(D, I, Dr, Ir, X, Q, tie_tol=TIE_TOL_BF16)
+        assert rep["ok"], rep
+    a.close()
+    b.close()
+
+
+def test_tensor_other_dims(pkg, oracle):
+    for d in (128, 256, 512, 768, 1024):
+        X, Q = unit_rows(5000, d, d + 3), unit_rows(40, d, d + 4)
+        idx = build(pkg, X, path=2)
+        D, I = idx.search(Q, 10)
+        Xb, Qb = oracle.round_bf16(X), oracle.round_bf16(Q)
+        Dr, Ir = oracle.flat_ip_topk(Xb, Qb, 10)
+        rep = oracle.compare_topk(D, I, Dr, Ir, Xb, Qb, tie_tol=TIE_TOL_F32)
+        assert rep["ok"], (d, rep)
+        idx.close()
