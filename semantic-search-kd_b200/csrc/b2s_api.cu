@@ -207,6 +207,7 @@ bool dim_supported(int dim) {
 }
 
 int launch_merge(const MergeParams& mp, int nq, cudaStream_t s) {
+    if (mp.num_lists > kMergeMaxLists) return fail(B2S_ERR_UNSUPPORTED, "too many candidate lists per query");
     merge_topk_kernel<<<nq, kMergeThreads, 0, s>>>(mp);
     CUDA_TRY(cudaGetLastError());
     return B2S_OK;
@@ -221,8 +222,8 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
     int grid = idx->num_sms * std::max(1, idx->opt_scan_ctas_per_sm);
     const int64_t units = (idx->n + unit - 1) / unit;
     if ((int64_t)grid > units) grid = (int)units;
+    grid = std::min(grid, kMergeMaxLists);
     const int64_t rows_per_cta = ((units + grid - 1) / grid) * unit;
-    grid = (int)((idx->n + rows_per_cta - 1) / rows_per_cta);
     const int max_group = scan_max_nq(idx->dim);
 
     const int chunk = (int)std::min<int64_t>(nq, kScanQueryChunk);

@@ -56,10 +56,25 @@ __device__ __forceinline__ void block_sort_desc(u64* buf, int m, int tid) {
     bitonic_sort_desc(buf, n, tid, kMergeThreads, BlockSync());
 }
 
+constexpr int kMergeMaxLists = 1024;  // candidate lists per query (CTAs of the producing kernel)
+
+// Position e of the concatenation of all lists -> its key.  offs[] = exclusive prefix sums of the
+// list counts (shared memory); a binary search finds the list, so every thread's load is
+// independent of every other (one DRAM/L2 round trip for the whole gather instead of one per list).
+__device__ __forceinline__ u64 fetch_candidate(const MergeParams& p, const int* offs, int L, int q, int e) {
+    int lo = 0, hi = L;  // largest l with offs[l] <= e
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (offs[mid] <= e) lo = mid;
+        else hi = mid;
+    }
+    return p.lists[((size_t)lo * p.nq_lists + q) * p.cap + (e - offs[lo])];
+}
+
 __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergeParams p) {
     __shared__ u64 buf[kMergeSortCap];
+    __shared__ int offs[kMergeMaxLists + 1];
     __shared__ int hist[kRadixBins];
-    __shared__ int s_total;
     __shared__ int s_fill;
     __shared__ u64 s_prefix;      // selected high bits so far
     __shared__ int s_bits_done;   // number of high bits fixed in s_prefix
@@ -68,33 +83,35 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergePa
 
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
-    const int L = p.num_lists;
+    const int L = p.num_lists;    // host guarantees L <= kMergeMaxLists
 
+    // exclusive prefix sums of the per-list counts (Hillis-Steele in shared memory)
+    for (int l = tid; l < L; l += kMergeThreads) offs[l + 1] = p.counts[(size_t)l * p.nq_lists + q];
     if (tid == 0) {
-        s_total = 0;
+        offs[0] = 0;
         s_fill = 0;
     }
     __syncthreads();
-    // total candidate count
-    int local = 0;
-    for (int l = tid; l < L; l += kMergeThreads) local += p.counts[(size_t)l * p.nq_lists + q];
-    if (local) atomicAdd(&s_total, local);
-    __syncthreads();
-    const int M = s_total;
+    for (int d = 1; d < L; d <<= 1) {
+        int add[kMergeMaxLists / kMergeThreads];
+#pragma unroll
+        for (int r = 0; r < kMergeMaxLists / kMergeThreads; ++r) {
+            const int l = tid + r * kMergeThreads + 1;
+            add[r] = (l <= L && l - d >= 1) ? offs[l - d] : 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kMergeMaxLists / kMergeThreads; ++r) {
+            const int l = tid + r * kMergeThreads + 1;
+            if (l <= L) offs[l] += add[r];
+        }
+        __syncthreads();
+    }
+    const int M = offs[L];
     int m_sorted;  // number of valid keys in buf after the gather
 
     if (M <= kMergeSortCap) {
-        // gather everything (order irrelevant: it is sorted next)
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int l = warp; l < L; l += kMergeThreads / 32) {
-            const int c = p.counts[(size_t)l * p.nq_lists + q];
-            if (c == 0) continue;
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_fill, c);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const u64* src = p.lists + ((size_t)l * p.nq_lists + q) * p.cap;
-            for (int i = lane; i < c; i += 32) buf[base + i] = src[i];
-        }
+        for (int e = tid; e < M; e += kMergeThreads) buf[e] = fetch_candidate(p, offs, L, q, e);
         __syncthreads();
         m_sorted = M;
     } else {
@@ -116,14 +133,10 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergePa
             const u64 prefix = s_prefix;
             for (int i = tid; i < kRadixBins; i += kMergeThreads) hist[i] = 0;
             __syncthreads();
-            for (int l = 0; l < L; ++l) {
-                const int c = p.counts[(size_t)l * p.nq_lists + q];
-                const u64* src = p.lists + ((size_t)l * p.nq_lists + q) * p.cap;
-                for (int i = tid; i < c; i += kMergeThreads) {
-                    const u64 key = src[i];
-                    const bool in_bucket = bits_done == 0 || (key >> (64 - bits_done)) == prefix;
-                    if (in_bucket) atomicAdd(&hist[(int)((key >> shift) & ((1u << nbits) - 1u))], 1);
-                }
+            for (int e = tid; e < M; e += kMergeThreads) {
+                const u64 key = fetch_candidate(p, offs, L, q, e);
+                const bool in_bucket = bits_done == 0 || (key >> (64 - bits_done)) == prefix;
+                if (in_bucket) atomicAdd(&hist[(int)((key >> shift) & ((1u << nbits) - 1u))], 1);
             }
             __syncthreads();
             if (tid == 0) {
@@ -144,16 +157,12 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergePa
         // gather winners (prefix bits above the bucket) and the bucket itself
         const int bits_done = s_bits_done;
         const u64 prefix = s_prefix;
-        for (int l = 0; l < L; ++l) {
-            const int c = p.counts[(size_t)l * p.nq_lists + q];
-            const u64* src = p.lists + ((size_t)l * p.nq_lists + q) * p.cap;
-            for (int i = tid; i < c; i += kMergeThreads) {
-                const u64 key = src[i];
-                const bool take = bits_done == 0 || (key >> (64 - bits_done)) >= prefix;
-                if (take) {
-                    int pos = atomicAdd(&s_fill, 1);
-                    if (pos < kMergeSortCap) buf[pos] = key;
-                }
+        for (int e = tid; e < M; e += kMergeThreads) {
+            const u64 key = fetch_candidate(p, offs, L, q, e);
+            const bool take = bits_done == 0 || (key >> (64 - bits_done)) >= prefix;
+            if (take) {
+                const int pos = atomicAdd(&s_fill, 1);
+                if (pos < kMergeSortCap) buf[pos] = key;
             }
         }
         __syncthreads();

@@ -26,7 +26,7 @@ struct ScanParams {
     const uint4* corpus;   // bf16 rows, row-major, dim*2 bytes each (16-byte aligned)
     const float* queries;  // fp32 [nq_total, dim]; this launch uses rows q_begin .. q_begin+NQ-1
     long long n_rows;      // rows in the shard
-    long long rows_per_cta;  // multiple of the unit (2U rows * kScanWarps)
+    long long rows_per_cta;  // unused by the grid-stride schedule (kept for diagnostics)
     int q_begin;
     int nq_valid;          // how many of the NQ register queries are real (others masked)
     int k;
@@ -101,9 +101,11 @@ scan_topk_kernel(const ScanParams p) {
     }
     __syncthreads();
 
-    const long long row_begin = (long long)blockIdx.x * p.rows_per_cta;
-    long long row_end = row_begin + p.rows_per_cta;
-    if (row_end > p.n_rows) row_end = p.n_rows;
+    // Grid-stride schedule: a "unit" is kScanWarps * 2U consecutive rows (48 KB at dim 384); CTA b
+    // takes units b, b + G, b + 2G, ...  At any moment the whole grid therefore reads one compact
+    // window of G units (~14 MB), which keeps DRAM pages and the 2 MB-page TLB hot -- unlike a
+    // contiguous per-CTA partition, where G distant regions stream at once.
+    const long long row_end = p.n_rows;
     const long long last_row = p.n_rows - 1;
 
     // Rare path, kept out of line of the hot loop: pick the row this lane speaks for (lane hl < U
@@ -124,8 +126,9 @@ scan_topk_kernel(const ScanParams p) {
         }
     };
 
-    const long long step = (long long)kScanWarps * kRowsPerIter * p.unit_stride;
-    long long base = row_begin + (long long)warp * kRowsPerIter * p.unit_stride;
+    constexpr long long kUnitRows = (long long)kScanWarps * kRowsPerIter;
+    const long long step = kUnitRows * (long long)gridDim.x * p.unit_stride;
+    long long base = kUnitRows * (long long)blockIdx.x * p.unit_stride + (long long)warp * kRowsPerIter;
     // lane's pointer to chunk hl of row (base + half); advanced by `step` rows per iteration
     const uint4* rp = p.corpus + (base + half) * kChunksPerRow + hl;
     const long long rp_step = step * kChunksPerRow;

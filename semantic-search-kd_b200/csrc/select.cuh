@@ -81,8 +81,11 @@ struct ListRef {
     int* lock;      // 0 free, 1 held
 };
 
+// seed_key (optional) is the k-th best key of a row SAMPLE of the same shard: every final top-k
+// key is >= it, so the threshold is made inclusive (seed - 1) -- the sampled row itself is
+// scanned again by the main pass and must still be accepted.
 __device__ __forceinline__ void list_init(const ListRef& st, u64 seed_key) {
-    *st.thr_key = seed_key;
+    *st.thr_key = seed_key ? seed_key - 1ull : 0ull;
     *st.thr = seed_key ? key_score(seed_key) : -INFINITY;
     *st.count = 0;
     *st.lock = 0;
