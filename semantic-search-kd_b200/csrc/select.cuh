@@ -44,21 +44,44 @@ __host__ __device__ inline int list_capacity(int k) {
     return c;
 }
 
-// In-place bitonic sort, DESCENDING, of a[0..n) (n a power of two) by `nthreads` cooperating
-// threads with ids tid in [0, nthreads).  `sync` is __syncwarp or __syncthreads.
+// ---------------------------------------------------------------------------------------------
+// Lane-uniform building blocks.  Everything below is written so that NO branch depends on the
+// lane id or on per-lane data: per-lane effects are predicated instructions or selects, loop trip
+// counts are warp-uniform.  A warp that never diverges never needs to reconverge -- which matters
+// twice: the hot loops stay on the converged fast path of every warp collective, and the tensor
+// path's tcgen05.ld.sync.aligned is only defined for a converged warp.
+// ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+// if (pred) *ptr = v;   (generic address, no branch)
+__device__ __forceinline__ void st_u64_if(u64* ptr, u64 v, bool pred) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.u32 p, %2, 0;\n\t"
+        "@p st.u64 [%0], %1;\n\t"
+        "}\n"
+        ::"l"(ptr), "l"(v), "r"((uint32_t)pred)
+        : "memory");
+}
+
+// In-place bitonic sort, DESCENDING, of a[0..n) (n a power of two, n/2 a multiple of nthreads)
+// by `nthreads` cooperating threads with ids tid in [0, nthreads).  `sync` is __syncwarp or
+// __syncthreads.  Compare-exchange is select + unconditional stores.
 template <typename SyncFn>
 __device__ __forceinline__ void bitonic_sort_desc(u64* a, int n, int tid, int nthreads, SyncFn sync) {
     for (int size = 2; size <= n; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             for (int i = tid; i < (n >> 1); i += nthreads) {
-                int lo = 2 * i - (i & (stride - 1));
-                int hi = lo + stride;
-                bool desc = (lo & size) == 0;
-                u64 x = a[lo], y = a[hi];
-                if ((x < y) == desc) {
-                    a[lo] = y;
-                    a[hi] = x;
-                }
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const u64 x = a[lo], y = a[hi];
+                const bool sw = (x < y) == desc;
+                a[lo] = sw ? y : x;
+                a[hi] = sw ? x : y;
             }
             sync();
         }
@@ -78,7 +101,7 @@ struct ListRef {
     u64* thr_key;   // a candidate must have key > *thr_key
     float* thr;     // fast test: score >= *thr  (score of thr_key, -inf when unset)
     int* count;     // entries currently in the list
-    int* lock;      // 0 free, 1 held
+    int* lock;      // 0 free, 1 held (shared memory)
 };
 
 // seed_key (optional) is the k-th best key of a row SAMPLE of the same shard: every final top-k
@@ -97,49 +120,64 @@ __device__ __forceinline__ void list_disable(const ListRef& st) {  // masked que
     *st.lock = 0;
 }
 
+// Warp-collective spin lock in shared memory: lane 0 issues the CAS under a predicate, the result
+// is broadcast, the retry loop is warp-uniform.
 __device__ __forceinline__ void spin_acquire(int* lock, int lane) {
-    if (lane == 0) {
-        while (atomicCAS(lock, 0, 1) != 0) __nanosleep(32);
-    }
-    __syncwarp();
+    const uint32_t addr = smem_addr_u32(lock);
+    uint32_t old;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.eq.u32 p, %2, 0;\n\t"
+            "mov.u32 %0, 1;\n\t"
+            "@p atom.shared.cas.b32 %0, [%1], 0, 1;\n\t"
+            "}\n"
+            : "=r"(old)
+            : "r"(addr), "r"((uint32_t)lane)
+            : "memory");
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old != 0) __nanosleep(32);
+    } while (old != 0);
     __threadfence_block();
 }
 __device__ __forceinline__ void spin_release(int* lock, int lane) {
+    (void)lane;
     __threadfence_block();
     __syncwarp();
-    if (lane == 0) atomicExch(lock, 0);
+    *(volatile int*)lock = 0;   // every lane stores the same value: no lane predicate, no branch
     __syncwarp();
 }
 
 // One warp keeps the best k of entries[0..count) and publishes the new threshold.  The sort runs
-// in `work` (shared memory, >= cap slots): for a shared-memory list work == entries; for a
+// in `work` (shared memory, cap slots): for a shared-memory list work == entries; for a
 // global-memory list the keys are staged through the CTA's scratch buffer (scratch_lock).
-// Caller holds the list lock.  Returns the new count.
+// cap is a power of two >= 64.  Caller holds the list lock.  Returns the new count.
 __device__ __forceinline__ int list_compact_warp(const ListRef& st, u64* entries, int cap, int k, int lane,
                                                  u64* scratch = nullptr, int* scratch_lock = nullptr) {
     const int c = *(volatile int*)st.count;
     u64* work = entries;
-    if (scratch != nullptr) {
+    if (scratch != nullptr) {   // uniform
         spin_acquire(scratch_lock, lane);
-        for (int i = lane; i < c; i += 32) scratch[i] = entries[i];
         work = scratch;
     }
-    for (int i = c + lane; i < cap; i += 32) work[i] = 0ull;
+    for (int i = lane; i < cap; i += 32) {
+        const u64 v = entries[i];          // slots >= c hold stale keys: masked to 0
+        work[i] = (i < c) ? v : 0ull;
+    }
     __syncwarp();
     bitonic_sort_desc(work, cap, lane, 32, WarpSync());
     const int keep = c < k ? c : k;
     if (scratch != nullptr) {
-        for (int i = lane; i < keep; i += 32) entries[i] = work[i];
+        for (int i = lane; i < cap; i += 32) st_u64_if(entries + i, work[i], i < keep);
     }
     __syncwarp();
-    if (lane == 0) {
-        if (c >= k) {
-            const u64 kth = work[k - 1];
-            *(volatile u64*)st.thr_key = kth;
-            *(volatile float*)st.thr = key_score(kth);
-        }
-        *(volatile int*)st.count = keep;
+    if (c >= k) {   // uniform; every lane stores the same values
+        const u64 kth = work[k - 1];
+        *(volatile u64*)st.thr_key = kth;
+        *(volatile float*)st.thr = key_score(kth);
     }
+    *(volatile int*)st.count = keep;
     __syncwarp();
     if (scratch != nullptr) spin_release(scratch_lock, lane);
     return keep;
@@ -155,18 +193,19 @@ __device__ __forceinline__ void list_append_warp(const ListRef& st, u64* entries
     pass = pass && (key > tk);
     unsigned m = __ballot_sync(0xffffffffu, pass);
     int n = __popc(m);
-    if (n) {
+    if (n) {   // uniform
         int c = *(volatile int*)st.count;
-        if (c + n > cap) {
+        if (c + n > cap) {   // uniform
             c = list_compact_warp(st, entries, cap, k, lane, scratch, scratch_lock);
             tk = *(volatile u64*)st.thr_key;
             pass = pass && (key > tk);
             m = __ballot_sync(0xffffffffu, pass);
             n = __popc(m);
         }
-        if (pass) entries[c + __popc(m & ((1u << lane) - 1u))] = key;
+        const int slot = c + __popc(m & ((1u << lane) - 1u));
+        st_u64_if(entries + (pass ? slot : 0), key, pass);
         __syncwarp();
-        if (lane == 0) *(volatile int*)st.count = c + n;
+        *(volatile int*)st.count = c + n;
     }
     spin_release(st.lock, lane);
 }
