@@ -18,7 +18,7 @@ namespace b2s {
 
 constexpr int kMergeThreads = 512;
 constexpr int kMergeSortCap = 4096;  // keys (32 KB of shared memory)
-constexpr int kRadixBits = 11;
+constexpr int kRadixBits = 10;
 constexpr int kRadixBins = 1 << kRadixBits;
 
 struct MergeParams {
@@ -56,30 +56,36 @@ __device__ __forceinline__ void block_sort_desc(u64* buf, int m, int tid) {
     bitonic_sort_desc(buf, n, tid, kMergeThreads, BlockSync());
 }
 
-constexpr int kMergeMaxLists = 1024;  // candidate lists per query (CTAs of the producing kernel)
+constexpr int kMergeMaxLists = 512;   // candidate lists per query (CTAs of the producing kernel)
+constexpr int kMergeFastCap = 512;    // survivors the rank-sort fast path can hold
 
 // Position e of the concatenation of all lists -> its key.  offs[] = exclusive prefix sums of the
 // list counts (shared memory); a binary search finds the list, so every thread's load is
 // independent of every other (one DRAM/L2 round trip for the whole gather instead of one per list).
-__device__ __forceinline__ u64 fetch_candidate(const MergeParams& p, const int* offs, int L, int q, int e) {
+__device__ __forceinline__ u64 fetch_candidate(const MergeParams& p, const int* offs, int L, int q, int e,
+                                               int* list_out = nullptr) {
     int lo = 0, hi = L;  // largest l with offs[l] <= e
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         if (offs[mid] <= e) lo = mid;
         else hi = mid;
     }
+    if (list_out) *list_out = lo;
     return p.lists[((size_t)lo * p.nq_lists + q) * p.cap + (e - offs[lo])];
 }
 
 __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergeParams p) {
     __shared__ u64 buf[kMergeSortCap];
     __shared__ int offs[kMergeMaxLists + 1];
-    __shared__ int hist[kRadixBins];
+    __shared__ __align__(16) int hist[kRadixBins];
     __shared__ int s_fill;
     __shared__ u64 s_prefix;      // selected high bits so far
     __shared__ int s_bits_done;   // number of high bits fixed in s_prefix
     __shared__ int s_k_rem;       // rank still to find inside the current bucket
     __shared__ int s_bucket_cnt;  // candidates inside the current bucket
+    __shared__ u64 sel[kMergeFastCap];
+    __shared__ u64 s_floor;
+    __shared__ int s_nonempty;
 
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
@@ -108,13 +114,68 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergePa
         __syncthreads();
     }
     const int M = offs[L];
-    int m_sorted;  // number of valid keys in buf after the gather
+    int m_sorted;  // number of valid keys in buf[0..) sorted descending at the end
+    bool sorted_done = false;
 
-    if (M <= kMergeSortCap) {
-        for (int e = tid; e < M; e += kMergeThreads) buf[e] = fetch_candidate(p, offs, L, q, e);
+    // ---- fast path ---------------------------------------------------------------------------
+    // The k-th largest of the per-list maxima ("heads") is a lower bound of the k-th largest key
+    // overall (the k largest heads are k distinct candidates), so only keys >= that floor can be
+    // in the answer -- typically ~2k of the M candidates.  They are compacted and rank-sorted
+    // (each thread counts the keys greater than its own): no 4096-wide bitonic network.
+    u64* heads = reinterpret_cast<u64*>(hist);   // [L] aliases the radix histogram (used later only)
+    for (int l = tid; l < L; l += kMergeThreads) heads[l] = 0ull;
+    if (tid == 0) {
+        s_floor = 0ull;
+        s_nonempty = 0;
+    }
+    __syncthreads();
+    for (int e = tid; e < M; e += kMergeThreads) {
+        int l;
+        const u64 key = fetch_candidate(p, offs, L, q, e, &l);
+        atomicMax(&heads[l], key);
+        if (M <= kMergeSortCap) buf[e] = key;
+    }
+    __syncthreads();
+    {
+        int mine = 0;
+        for (int l = tid; l < L; l += kMergeThreads) mine += heads[l] != 0ull;
+        if (mine) atomicAdd(&s_nonempty, mine);
+    }
+    __syncthreads();
+    if (s_nonempty >= p.k) {
+        for (int l = tid; l < L; l += kMergeThreads) {
+            const u64 h = heads[l];
+            int rank = 0;
+            for (int j = 0; j < L; ++j) rank += heads[j] > h;
+            if (rank == p.k - 1 && h != 0ull) s_floor = h;   // keys are unique: exactly one writer
+        }
+    }
+    __syncthreads();
+    const u64 floor_key = s_floor;
+    for (int e = tid; e < M; e += kMergeThreads) {
+        const u64 key = (M <= kMergeSortCap) ? buf[e] : fetch_candidate(p, offs, L, q, e);
+        if (key >= floor_key) {
+            const int pos = atomicAdd(&s_fill, 1);
+            if (pos < kMergeFastCap) sel[pos] = key;
+        }
+    }
+    __syncthreads();
+    const int C = s_fill;
+    if (C <= kMergeFastCap) {
+        __syncthreads();   // everyone has read s_fill / buf before buf is overwritten
+        for (int t = tid; t < C; t += kMergeThreads) {
+            const u64 key = sel[t];
+            int rank = 0;
+            for (int j = 0; j < C; ++j) rank += sel[j] > key;
+            buf[rank] = key;
+        }
         __syncthreads();
-        m_sorted = M;
+        m_sorted = C;
+        sorted_done = true;
+    } else if (M <= kMergeSortCap) {
+        m_sorted = M;   // buf already holds every candidate
     } else {
+        if (tid == 0) s_fill = 0;
         // MSB-first radix select of the k-th largest key
         if (tid == 0) {
             s_prefix = 0ull;
@@ -169,7 +230,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergePa
         m_sorted = s_fill < kMergeSortCap ? s_fill : kMergeSortCap;
     }
 
-    block_sort_desc(buf, m_sorted > 0 ? m_sorted : 1, tid);
+    if (!sorted_done) block_sort_desc(buf, m_sorted > 0 ? m_sorted : 1, tid);
 
     const int kk = m_sorted < p.k ? m_sorted : p.k;
     for (int i = tid; i < p.k; i += kMergeThreads) {
