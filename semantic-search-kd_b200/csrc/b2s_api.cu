@@ -100,7 +100,7 @@ struct b2s_index {
     int opt_keep_f32 = 0;
     int opt_rescore_pad = 32;
     int opt_timing = 0;
-    int opt_tc_min_nq = 5;
+    int opt_tc_min_nq = 3;
     // workspace
     DevBuf ws_lists, ws_counts, ws_seed, ws_qf32, ws_qbf16, ws_io_q, ws_io_scores, ws_io_ids, ws_tmp;
     void* pin_q = nullptr;
@@ -333,7 +333,10 @@ int search_impl(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, in
 #endif
     idx->stats.path = path;
     const bool normalize = idx->metric == B2S_METRIC_COSINE;
-    bool seed = idx->opt_seed == 1 || (idx->opt_seed < 0 && k >= 32 && idx->n >= (int64_t)1 << 20);
+    // Threshold seeding (a pre-pass over every 64th unit): pays for itself once the per-CTA cold
+    // start matters -- always on the tensor path (one list per query per CTA), for k >= 32 on the scan.
+    bool seed = idx->opt_seed == 1 ||
+                (idx->opt_seed < 0 && idx->n >= (int64_t)1 << 20 && (k >= 32 || path == B2S_PATH_TENSOR));
     idx->stats.seeded = seed ? 1 : 0;
 
     if (path == B2S_PATH_SCAN) {

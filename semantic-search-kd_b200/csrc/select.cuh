@@ -35,10 +35,11 @@ __device__ __forceinline__ u64 make_key(float s, uint32_t row) {
 __device__ __forceinline__ float key_score(u64 key) { return ord_to_score((uint32_t)(key >> 32)); }
 __device__ __forceinline__ uint32_t key_row(u64 key) { return ~(uint32_t)key; }
 
-// Smallest power of two >= max(2k, k + 64): room for one full warp of appends after a
-// compaction, and at least a doubling of rows seen between compactions.
+// Smallest power of two >= max(2k, k + 32), at least 64: room for one full warp of appends after
+// a compaction, and at least a doubling of rows seen between compactions.  Small lists keep the
+// compaction (a single-warp bitonic sort of `cap` keys) cheap and the thresholds fresh.
 __host__ __device__ inline int list_capacity(int k) {
-    int need = 2 * k > k + 64 ? 2 * k : k + 64;
+    int need = 2 * k > k + 32 ? 2 * k : k + 32;
     int c = 64;
     while (c < need) c <<= 1;
     return c;

@@ -35,6 +35,7 @@ def build(pkg, X, metric="inner_product", **opts):
 def check(oracle, idx, X, Q, k, tight=True, q_bf16=False):
     """q_bf16: the tensor path rounds the queries to bf16 as well (tcgen05 operands are bf16)."""
     D, I = idx.search(Q, k)
+    q_bf16 = q_bf16 or (Q.shape[0] > 0 and k > 0 and idx.ntotal > 0 and idx.stats()["path"] == 2)
     assert D.shape == (Q.shape[0], k) and I.shape == (Q.shape[0], k)
     assert D.dtype == np.float32 and I.dtype == np.int64
     Dr, Ir = oracle.flat_ip_topk(X, Q, k)
