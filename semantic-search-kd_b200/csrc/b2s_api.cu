@@ -101,8 +101,11 @@ struct b2s_index {
     int opt_rescore_pad = 32;
     int opt_timing = 0;
     int opt_tc_min_nq = 3;
+    int opt_tc_sample_div = 64;   // the threshold pre-pass samples 1 / this of the full tiles
+    int opt_tc_chunk_lo = 48;     // tiles per work item when several query blocks share the corpus
+    int opt_tc_chunk_hi = 96;
     // workspace
-    DevBuf ws_lists, ws_counts, ws_seed, ws_qf32, ws_qbf16, ws_io_q, ws_io_scores, ws_io_ids, ws_tmp;
+    DevBuf ws_lists, ws_counts, ws_thr, ws_gmax, ws_seed, ws_qf32, ws_qbf16, ws_io_q, ws_io_scores, ws_io_ids, ws_tmp;
     void* pin_q = nullptr;
     void* pin_out = nullptr;
     size_t pin_q_bytes = 0, pin_out_bytes = 0;
@@ -333,10 +336,11 @@ int search_impl(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, in
 #endif
     idx->stats.path = path;
     const bool normalize = idx->metric == B2S_METRIC_COSINE;
-    // Threshold seeding (a pre-pass over every 64th unit): pays for itself once the per-CTA cold
-    // start matters -- always on the tensor path (one list per query per CTA), for k >= 32 on the scan.
+    // Threshold seeding: on the scan path a pre-pass over every 64th unit pays for itself once the
+    // per-CTA cold start matters (k >= 32 on a large shard); the tensor path always bounds the
+    // k-th best score from a row sample first (its lists are private to one thread).
     bool seed = idx->opt_seed == 1 ||
-                (idx->opt_seed < 0 && idx->n >= (int64_t)1 << 20 && (k >= 32 || path == B2S_PATH_TENSOR));
+                (idx->opt_seed < 0 && (path == B2S_PATH_TENSOR || (idx->n >= (int64_t)1 << 20 && k >= 32)));
     idx->stats.seeded = seed ? 1 : 0;
 
     if (path == B2S_PATH_SCAN) {
@@ -449,6 +453,8 @@ B2S_API int b2s_destroy(b2s_index* idx) {
     idx->ws_lists.release();
     idx->ws_counts.release();
     idx->ws_seed.release();
+    idx->ws_thr.release();
+    idx->ws_gmax.release();
     idx->ws_qf32.release();
     idx->ws_qbf16.release();
     idx->ws_io_q.release();
@@ -594,6 +600,11 @@ B2S_API int b2s_set_option(b2s_index* idx, const char* name, int64_t value) {
         idx->ev_valid = false;
     } else if (s == "tc_min_nq") {
         idx->opt_tc_min_nq = (int)std::max<int64_t>(1, value);
+    } else if (s == "tc_sample_div") {
+        idx->opt_tc_sample_div = (int)std::min<int64_t>(1 << 20, std::max<int64_t>(1, value));
+    } else if (s == "tc_chunk_tiles") {
+        if (value < 1 || value > 4096) return fail(B2S_ERR_INVALID, "tc_chunk_tiles must be in [1, 4096]");
+        idx->opt_tc_chunk_lo = idx->opt_tc_chunk_hi = (int)value;
     } else {
         return fail(B2S_ERR_INVALID, "unknown option: " + s);
     }
@@ -610,6 +621,8 @@ B2S_API int64_t b2s_get_option(const b2s_index* idx, const char* name) {
     if (s == "rescore_pad") return idx->opt_rescore_pad;
     if (s == "timing") return idx->opt_timing;
     if (s == "tc_min_nq") return idx->opt_tc_min_nq;
+    if (s == "tc_sample_div") return idx->opt_tc_sample_div;
+    if (s == "tc_chunk_tiles") return idx->opt_tc_chunk_lo == idx->opt_tc_chunk_hi ? idx->opt_tc_chunk_lo : 0;
     if (s == "num_sms") return idx->num_sms;
     return -1;
 }

@@ -1,11 +1,11 @@
 // gemm_topk_host.inl -- host side of the tensor path (included by b2s_api.cu after b2s_index).
-// Builds the TMA tensor maps, sizes the pipeline to the shared-memory budget, launches K2 (and
-// the optional threshold-seeding pre-pass) and the per-query merge K3.
+// Builds the TMA tensor maps, sizes the pipeline to the shared-memory budget, plans the work
+// items, launches the threshold pre-pass (K2 in PREPASS mode + seed_select), the main pass (K2)
+// and the per-query merge K3.
 
 namespace {
 
 constexpr int kTcQueryChunk = 4096;   // queries per workspace round on the tensor path
-constexpr int kTcSeedStride = 64;
 
 int tc_init(b2s_index* idx) {
     TensorPathState& tc = idx->tc;
@@ -19,7 +19,10 @@ int tc_init(b2s_index* idx) {
         CUDA_TRY(cudaDeviceGetAttribute(&tc.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, idx->device));
     }
     if (!tc.attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc.max_smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      tc.max_smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      tc.max_smem_optin));
         tc.attr_set = true;
     }
     return B2S_OK;
@@ -37,16 +40,21 @@ int tc_encode_rows(b2s_index* idx, CUtensorMap* map, const void* base, uint64_t 
     return B2S_OK;
 }
 
-// Largest query block (32 | 64 | 128) whose resident bf16 copy leaves room for >= 4 pipeline stages.
-int tc_pick_ntile(const b2s_index* idx, int64_t nq, int cap) {
-    const int kblocks = idx->dim / kTcKBlock;
-    int nt = nq <= 32 ? 32 : (nq <= 64 ? 64 : 128);
-    while (nt > 32) {
-        const TcSmemLayout L = tc_smem_layout(kblocks, nt, 4, cap);
-        if ((int)L.total + 1024 <= idx->tc.max_smem_optin) break;
-        nt >>= 1;
+// Tiles per work item in [lo, hi] that minimises the makespan (rounds x tiles) of dealing
+// ceil(tiles / c) * qblocks equal items round-robin to `pairs` CTA pairs.
+int tc_pick_chunk(int tiles, int qblocks, int pairs, int lo, int hi) {
+    int best = lo;
+    long long best_cost = -1;
+    for (int c = lo; c <= hi; ++c) {
+        const long long items = (long long)((tiles + c - 1) / c) * qblocks;
+        const long long rounds = (items + pairs - 1) / pairs;
+        const long long cost = rounds * c;
+        if (best_cost < 0 || cost < best_cost || (cost == best_cost && c > best)) {
+            best_cost = cost;
+            best = c;
+        }
     }
-    return nt;
+    return best;
 }
 
 int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, int k, float* out_scores,
@@ -57,28 +65,40 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
     const int cap = list_capacity(k);
     const int kblocks = idx->dim / kTcKBlock;
     if (!tc.corpus_map_valid) {
-        if ((rc = tc_encode_rows(idx, &tc.corpus_map, idx->rows, (uint64_t)idx->n, kTcTileRows)) != B2S_OK) return rc;
+        if ((rc = tc_encode_rows(idx, &tc.corpus_map, idx->rows, (uint64_t)idx->n, kTcRowsPerCta)) != B2S_OK) return rc;
         tc.corpus_map_valid = true;
     }
-    const int num_tiles = (int)((idx->n + kTcTileRows - 1) / kTcTileRows);
+    const int pairs = std::max(1, idx->num_sms / 2);
+    const int num_lists = 2 * pairs;
+    if (num_lists > kMergeMaxLists) return fail(B2S_ERR_UNSUPPORTED, "too many SMs for the merge kernel");
+    const int tiles_all = (int)((idx->n + kTcTileRows - 1) / kTcTileRows);
+    const int tiles_full = (int)(idx->n / kTcTileRows);
+
+    // pipeline depth from the shared-memory budget
+    int stages = kTcMaxStages;
+    while (stages > 2 && (int)tc_smem_layout(kblocks, stages).total + 1024 > tc.max_smem_optin) --stages;
+    const TcSmemLayout L = tc_smem_layout(kblocks, stages);
+    if ((int)L.total + 1024 > tc.max_smem_optin)
+        return fail(B2S_ERR_UNSUPPORTED, "tensor path: shared memory budget exceeded for this dim");
+
+    // threshold pre-pass: a sample of full tiles whose 32-row group maxima bound the k-th best score
+    int sample_tiles = 0, sample_stride = 1;
+    if (seed && tiles_full > 0) {
+        const int want_groups = std::max(1024, 8 * k);
+        int ts = std::max((tiles_full + idx->opt_tc_sample_div - 1) / idx->opt_tc_sample_div,
+                          (want_groups + kTcGroupsPerTile - 1) / kTcGroupsPerTile);
+        ts = std::min(ts, tiles_full);
+        sample_stride = std::max(1, tiles_full / ts);
+        sample_tiles = (tiles_full + sample_stride - 1) / sample_stride;
+        if (sample_tiles * kTcGroupsPerTile < k) sample_tiles = 0;
+    }
+    const int groups = sample_tiles * kTcGroupsPerTile;
+    idx->stats.seeded = sample_tiles > 0 ? 1 : 0;
 
     for (int64_t c0 = 0; c0 < nq; c0 += kTcQueryChunk) {
         const int cn = (int)std::min<int64_t>(kTcQueryChunk, nq - c0);
-        const int n_tile = tc_pick_ntile(idx, cn, cap);
-        const int nqb = (cn + n_tile - 1) / n_tile;
-        const int nq_pad = nqb * n_tile;
-        // pipeline depth from the shared-memory budget
-        int stages = kTcMaxStages;
-        while (stages > 2 && (int)tc_smem_layout(kblocks, n_tile, stages, cap).total + 1024 > tc.max_smem_optin) --stages;
-        const TcSmemLayout L = tc_smem_layout(kblocks, n_tile, stages, cap);
-        if ((int)L.total + 1024 > tc.max_smem_optin)
-            return fail(B2S_ERR_UNSUPPORTED, "tensor path: shared memory budget exceeded for this (dim, k)");
-        // slices of the corpus: fill the SMs once the query blocks are accounted for
-        int slices = std::max(1, idx->num_sms / nqb);
-        if (nqb > 1 && nqb < idx->num_sms) slices = std::max(1, (2 * idx->num_sms) / nqb);   // two waves
-        slices = std::min(slices, num_tiles);
-        const int tiles_per_slice = (num_tiles + slices - 1) / slices;
-        slices = (num_tiles + tiles_per_slice - 1) / tiles_per_slice;
+        const int qblocks = (cn + kTcQueriesPerPair - 1) / kTcQueriesPerPair;
+        const int nq_pad = qblocks * kTcQueriesPerPair;
 
         // queries -> bf16 [nq_pad, dim], zero padded, optionally normalised
         if ((rc = idx->ws_qbf16.ensure((size_t)nq_pad * idx->dim * 2)) != B2S_OK) return rc;
@@ -93,54 +113,76 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
             idx->stats.kernel_launches++;
         }
         CUtensorMap qmap;
-        if ((rc = tc_encode_rows(idx, &qmap, idx->ws_qbf16.p, (uint64_t)nq_pad, (uint32_t)n_tile)) != B2S_OK) return rc;
+        if ((rc = tc_encode_rows(idx, &qmap, idx->ws_qbf16.p, (uint64_t)nq_pad, kTcQueriesPerCta)) != B2S_OK) return rc;
 
-        if ((rc = idx->ws_lists.ensure((size_t)slices * nq_pad * cap * sizeof(u64))) != B2S_OK) return rc;
-        if ((rc = idx->ws_counts.ensure((size_t)slices * nq_pad * sizeof(int))) != B2S_OK) return rc;
-        if (seed && (rc = idx->ws_seed.ensure((size_t)nq_pad * sizeof(u64))) != B2S_OK) return rc;
+        const size_t n_state = (size_t)num_lists * nq_pad;
+        if ((rc = idx->ws_lists.ensure(n_state * cap * sizeof(u64))) != B2S_OK) return rc;
+        if ((rc = idx->ws_counts.ensure(n_state * sizeof(int))) != B2S_OK) return rc;
+        if ((rc = idx->ws_thr.ensure(n_state * sizeof(u64))) != B2S_OK) return rc;
+        if ((rc = idx->ws_seed.ensure((size_t)nq_pad * sizeof(u64))) != B2S_OK) return rc;
+        if (sample_tiles > 0 && (rc = idx->ws_gmax.ensure((size_t)nq_pad * groups * sizeof(float))) != B2S_OK) return rc;
 
-        if (idx->opt_timing && c0 == 0) cudaEventRecord(idx->ev[1], s);
-        for (int pass = seed ? 0 : 1; pass < 2; ++pass) {
-            TcParams p;
-            p.n_rows = idx->n;
-            p.num_tiles = num_tiles;
-            p.tiles_per_slice = tiles_per_slice;
-            p.tile_stride = pass == 0 ? kTcSeedStride : 1;
-            p.kblocks = kblocks;
-            p.n_tile = n_tile;
-            p.stages = stages;
-            p.nq = cn;
-            p.nq_pad = nq_pad;
-            p.k = k;
-            p.cap = cap;
-            p.seed_keys = (pass == 1 && seed) ? reinterpret_cast<const u64*>(idx->ws_seed.p) : nullptr;
-            p.lists = reinterpret_cast<u64*>(idx->ws_lists.p);
-            p.counts = reinterpret_cast<int*>(idx->ws_counts.p);
-            dim3 grid((unsigned)slices, (unsigned)nqb, 1);
-            gemm_topk_kernel<<<grid, kTcThreads, L.total + 1024, s>>>(tc.corpus_map, qmap, p);
+        TcParams p;
+        memset(&p, 0, sizeof(p));
+        p.n_rows = (uint32_t)idx->n;
+        p.qblocks = qblocks;
+        p.kblocks = kblocks;
+        p.stages = stages;
+        p.nq = cn;
+        p.nq_pad = nq_pad;
+        p.k = k;
+        p.cap = cap;
+        p.policy = qblocks > 1 ? ptx::kEvictNormal : ptx::kEvictFirst;
+        p.lists = reinterpret_cast<u64*>(idx->ws_lists.p);
+        p.counts = reinterpret_cast<int*>(idx->ws_counts.p);
+        p.thr_keys = reinterpret_cast<u64*>(idx->ws_thr.p);
+        const dim3 grid((unsigned)(2 * pairs), 1, 1);
+
+        if (sample_tiles > 0) {
+            TcParams pp = p;
+            pp.tiles_total = sample_tiles;
+            pp.tile_mul = sample_stride;
+            pp.chunk_tiles = tc_pick_chunk(sample_tiles, qblocks, pairs, 1, 16);
+            pp.num_chunks = (sample_tiles + pp.chunk_tiles - 1) / pp.chunk_tiles;
+            pp.policy = ptx::kEvictNormal;
+            pp.gmax = reinterpret_cast<float*>(idx->ws_gmax.p);
+            pp.groups = groups;
+            gemm_topk_kernel<true><<<grid, kTcThreads, L.total + 1024, s>>>(tc.corpus_map, qmap, pp);
             CUDA_TRY(cudaGetLastError());
-            idx->stats.kernel_launches++;
-            if (pass == 1) idx->stats.passes += nqb;
-            if (pass == 1 && idx->opt_timing && c0 == 0) cudaEventRecord(idx->ev[2], s);
-
-            MergeParams mp;
-            memset(&mp, 0, sizeof(mp));
-            mp.lists = reinterpret_cast<const u64*>(idx->ws_lists.p);
-            mp.counts = reinterpret_cast<const int*>(idx->ws_counts.p);
-            mp.num_lists = slices;
-            mp.nq_lists = nq_pad;
-            mp.cap = cap;
-            mp.k = k;
-            mp.id_offset = idx->id_offset;
-            if (pass == 0) {
-                mp.out_kth_key = reinterpret_cast<u64*>(idx->ws_seed.p);
-            } else {
-                mp.out_scores = out_scores + (size_t)c0 * k;
-                mp.out_ids = reinterpret_cast<long long*>(out_ids) + (size_t)c0 * k;
-            }
-            if ((rc = launch_merge(mp, cn, s)) != B2S_OK) return rc;
-            idx->stats.kernel_launches++;
+            seed_select_kernel<<<(unsigned)nq_pad, kSeedThreads, 0, s>>>(pp.gmax, groups, k,
+                                                                         reinterpret_cast<u64*>(idx->ws_seed.p));
+            CUDA_TRY(cudaGetLastError());
+            idx->stats.kernel_launches += 2;
+            p.seed_keys = reinterpret_cast<const u64*>(idx->ws_seed.p);
         }
+
+        CUDA_TRY(cudaMemsetAsync(idx->ws_counts.p, 0, n_state * sizeof(int), s));
+        CUDA_TRY(cudaMemsetAsync(idx->ws_thr.p, 0, n_state * sizeof(u64), s));
+        p.tiles_total = tiles_all;
+        p.tile_mul = 1;
+        p.chunk_tiles = qblocks > 1 ? tc_pick_chunk(tiles_all, qblocks, pairs, idx->opt_tc_chunk_lo, idx->opt_tc_chunk_hi)
+                                    : tc_pick_chunk(tiles_all, 1, pairs, 8, 32);
+        p.num_chunks = (tiles_all + p.chunk_tiles - 1) / p.chunk_tiles;
+        if (idx->opt_timing && c0 == 0) cudaEventRecord(idx->ev[1], s);
+        gemm_topk_kernel<false><<<grid, kTcThreads, L.total + 1024, s>>>(tc.corpus_map, qmap, p);
+        CUDA_TRY(cudaGetLastError());
+        idx->stats.kernel_launches++;
+        idx->stats.passes += qblocks;
+        if (idx->opt_timing && c0 == 0) cudaEventRecord(idx->ev[2], s);
+
+        MergeParams mp;
+        memset(&mp, 0, sizeof(mp));
+        mp.lists = reinterpret_cast<const u64*>(idx->ws_lists.p);
+        mp.counts = reinterpret_cast<const int*>(idx->ws_counts.p);
+        mp.num_lists = num_lists;
+        mp.nq_lists = nq_pad;
+        mp.cap = cap;
+        mp.k = k;
+        mp.id_offset = idx->id_offset;
+        mp.out_scores = out_scores + (size_t)c0 * k;
+        mp.out_ids = reinterpret_cast<long long*>(out_ids) + (size_t)c0 * k;
+        if ((rc = launch_merge(mp, cn, s)) != B2S_OK) return rc;
+        idx->stats.kernel_launches++;
     }
     return B2S_OK;
 }

@@ -1,24 +1,37 @@
 // gemm_topk_tc.cuh -- K2: batched exact inner-product search on the 5th-gen tensor cores with a
-// fused top-k epilogue (the [N x B] score matrix never exists outside TMEM).
+// fused top-k epilogue (the [nq x N] score matrix never exists outside TMEM).
 //
 // Replaces the reference's dense contraction + per-row sort for query batches:
 //   np.matmul(query_embs, corpus_embs.T) + argsort   (/root/reference/scripts/simple_eval.py:25,35)
 //   compute_similarity(q, corpus)[0] + argsort        (/root/reference/src/kd/eval.py:75,86)
 //   faiss IndexFlatIP's blocked sgemm + heap path behind FAISSIndexBuilder.search.
 //
-// Layout ("swap-AB"): the 128 corpus rows of a tile are the MMA M dimension (A operand, streamed
-// HBM -> shared memory by TMA in 128-row x 64-element SWIZZLE_128B boxes, 16 KB per pipeline
-// stage); the CTA's query block (n_tile <= 128 queries, bf16) is the N dimension (B operand),
-// loaded once and kept resident in shared memory; K = dim is consumed 64 elements per stage as 4
-// tcgen05.mma (K = 16) instructions.  The fp32 accumulator tile [128 rows x n_tile queries] lives
-// in TMEM (row -> lane, query -> column), double buffered so the MMA of tile t+1 overlaps the
-// epilogue of tile t.
+// Shape of one MMA (tcgen05.mma.cta_group::2.kind::f16, M = 256, N = 256, K = 16): a CTA PAIR
+// (2-CTA cluster = one TPC) multiplies a resident block of 256 queries (A operand: 128 queries per
+// CTA, bf16, loaded once per work item and kept in shared memory) with a streamed tile of 256
+// corpus rows (B operand: each CTA TMA-loads ITS 128 rows, SWIZZLE_128B boxes of 128 rows x 64
+// elements = 16 KB per pipeline stage).  Every corpus byte fetched from L2/HBM therefore meets 256
+// queries -- the bf16 machine balance of a B200 (flop/byte) -- while each SM only stages half of
+// the tile.  The fp32 accumulator [128 queries x 256 rows] of each CTA lives in its TMEM
+// (query -> lane, corpus row -> column), double buffered (2 x 256 = all 512 columns) so the MMAs
+// of tile t+1 overlap the epilogue of tile t.
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
-// warp 2 = TMEM allocator, warps 4-7 = epilogue: thread <-> corpus row; tcgen05.ld 32 query
-// columns at a time, compare against the per-query running thresholds (shared memory, broadcast
-// reads) and append the rare survivors to the CTA's per-query candidate lists (select.cuh; the
-// lists live in global memory / L2, compaction is staged through a shared-memory scratch).
+// Epilogue = the fused select.  An epilogue thread owns ONE query (its TMEM lane): its threshold
+// sits in a register, the test of a score is one FSETP against that register, and the rare
+// survivors are appended to a list that only this thread writes -- no locks, no atomics, no
+// shared-memory state.  Thresholds come from a pre-pass over a row sample (PREPASS = true: the
+// same pipeline, but the epilogue only reduces every 32-row group to its maximum; the k-th
+// largest group maximum is a lower bound of the k-th best score: seed_select_kernel).  If a list
+// still fills up (adversarial data, or no sample) its owner keeps the best k with a private
+// quickselect and raises its threshold, so the result is exact for any input.
+//
+// Work items = (corpus chunk, query block), chunk-major, dealt round-robin to the 74 pairs: pairs
+// that hold different query blocks walk the same chunk at the same time, so a chunk is fetched
+// from HBM once and re-read from the 126 MB L2 by the others.
+//
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only, one
+// elected lane), warp 2 = TMEM allocator, warps 4-11 = epilogue (warp w reads TMEM lanes
+// 32*(w%4).., column half (w-4)/4).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -29,82 +42,110 @@
 
 namespace b2s {
 
-constexpr int kTcThreads = 256;
-constexpr int kTcTileRows = 128;   // UMMA M
-constexpr int kTcKBlock = 64;      // bf16 elements per 128-byte swizzle row
-constexpr int kTcStageBytes = kTcTileRows * kTcKBlock * 2;  // 16 KB
+constexpr int kTcThreads = 384;
+constexpr int kTcEpiWarps = 8;
+constexpr int kTcQueriesPerCta = 128;   // UMMA M per CTA
+constexpr int kTcQueriesPerPair = 256;  // UMMA M
+constexpr int kTcRowsPerCta = 128;      // B rows staged by one CTA
+constexpr int kTcTileRows = 256;        // UMMA N = corpus rows per pair tile
+constexpr int kTcKBlock = 64;           // bf16 elements per 128-byte swizzle row
+constexpr int kTcStageBytes = kTcRowsPerCta * kTcKBlock * 2;     // 16 KB
+constexpr int kTcQBlockBytes = kTcQueriesPerCta * kTcKBlock * 2;  // 16 KB per k-block
 constexpr int kTcMaxStages = 10;
-constexpr int kTcMaxNTile = 128;
 constexpr int kTcAccStages = 2;
+constexpr int kTcGroupsPerTile = kTcTileRows / 32;   // 32-row groups whose maxima the pre-pass records
 
 struct TcParams {
-    long long n_rows;      // rows in the shard
-    int num_tiles;         // ceil(n_rows / 128)
-    int tiles_per_slice;   // contiguous tiles owned by one slice (blockIdx.x)
-    int tile_stride;       // 1 = every tile, S = every S-th tile (threshold-seeding pre-pass)
-    int kblocks;           // dim / 64
-    int n_tile;            // queries per CTA (32 | 64 | 128) = UMMA N
-    int stages;            // A-ring depth
-    int nq;                // real queries (columns >= nq are masked)
-    int nq_pad;            // gridDim.y * n_tile
+    uint32_t n_rows;        // rows in the shard
+    int tiles_total;        // tiles this launch iterates over (pre-pass: sampled tiles)
+    int tile_mul;           // actual tile = index * tile_mul (pre-pass sample stride; 1 otherwise)
+    int chunk_tiles;        // tiles per work item
+    int num_chunks;         // ceil(tiles_total / chunk_tiles)
+    int qblocks;            // query blocks of 256
+    int kblocks;            // dim / 64
+    int stages;             // B ring depth
+    int nq;                 // real queries (rows >= nq of the padded query matrix are zero / masked)
+    int nq_pad;             // qblocks * 256
     int k;
-    int cap;               // candidate list capacity (power of two)
-    const u64* seed_keys;  // optional [nq_pad] initial thresholds
-    u64* lists;            // [gridDim.x, nq_pad, cap]
-    int* counts;           // [gridDim.x, nq_pad]
+    int cap;                // candidate list capacity (>= 2k)
+    unsigned long long policy;   // L2 cache hint for corpus tiles
+    const u64* seed_keys;   // optional [nq_pad]: a candidate must have key > seed (0 = none)
+    u64* lists;             // [2 * pairs, nq_pad, cap]
+    int* counts;            // [2 * pairs, nq_pad]   (zeroed by the host before the main pass)
+    u64* thr_keys;          // [2 * pairs, nq_pad]   (zeroed by the host before the main pass)
+    float* gmax;            // pre-pass out: [nq_pad, groups] maxima of 32-row groups
+    int groups;             // tiles_total * 8 (pre-pass)
 };
 
-// dynamic shared memory carve-up (all offsets from a 1024-byte aligned base)
+// dynamic shared memory carve-up (all offsets from a 1024-byte aligned base; identical in both CTAs)
 struct TcSmemLayout {
-    uint32_t q_off, a_off, scratch_off, bar_off, state_off, total;
+    uint32_t q_off, b_off, bar_off, total;
 };
-__host__ __device__ inline TcSmemLayout tc_smem_layout(int kblocks, int n_tile, int stages, int cap) {
+__host__ __device__ inline TcSmemLayout tc_smem_layout(int kblocks, int stages) {
     TcSmemLayout L;
     L.q_off = 0;
-    L.a_off = (uint32_t)kblocks * n_tile * 128;                  // n_tile*128 is a multiple of 1024
-    L.scratch_off = L.a_off + (uint32_t)stages * kTcStageBytes;
-    L.bar_off = L.scratch_off + (uint32_t)cap * 8;
-    L.state_off = L.bar_off + 256;                              // <= 2*10 + 1 + 4 barriers of 8 bytes
-    L.total = L.state_off + (uint32_t)n_tile * (8 + 4 + 4 + 4) + 16;
+    L.b_off = (uint32_t)kblocks * kTcQBlockBytes;
+    L.bar_off = L.b_off + (uint32_t)stages * kTcStageBytes;
+    L.total = L.bar_off + 256;   // 2*10 + 2 + 4 barriers of 8 bytes + the TMEM base address
     return L;
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+// Keep the k largest keys of a[0..n) in a[0..k) (any order) and return the smallest of them.
+// Thread-private Hoare quickselect on unique keys; runs only when a list overflows.
+__device__ __noinline__ u64 list_keep_top_k(u64* a, int n, int k) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const u64 x = a[lo], y = a[(lo + hi) >> 1], z = a[hi];
+        const u64 pivot = x > y ? (y > z ? y : (x > z ? z : x)) : (x > z ? x : (y > z ? z : y));
+        int i = lo, j = hi;
+        while (i <= j) {
+            while (a[i] > pivot) ++i;
+            while (a[j] < pivot) --j;
+            if (i <= j) {
+                const u64 t = a[i];
+                a[i] = a[j];
+                a[j] = t;
+                ++i;
+                --j;
+            }
+        }
+        // a[lo..j] >= pivot >= a[i..hi]; positions j+1..i-1 (if any) hold the pivot
+        if (k - 1 <= j) hi = j;
+        else if (k - 1 >= i) lo = i;
+        else break;
+    }
+    u64 m = a[0];
+    for (int i = 1; i < k; ++i) m = a[i] < m ? a[i] : m;
+    return m;
+}
+
+template <bool PREPASS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_constant__ CUtensorMap map_queries,
                  const TcParams p) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
     // SWIZZLE_128B tiles need a 1024-byte aligned base; the launch adds 1024 bytes of slack
     unsigned char* smem = tc_smem_raw + ((1024u - (ptx::smem_u32(tc_smem_raw) & 1023u)) & 1023u);
-    const TcSmemLayout L = tc_smem_layout(p.kblocks, p.n_tile, p.stages, p.cap);
+    const TcSmemLayout L = tc_smem_layout(p.kblocks, p.stages);
     unsigned char* smem_q = smem + L.q_off;
-    unsigned char* smem_a = smem + L.a_off;
-    u64* scratch = reinterpret_cast<u64*>(smem + L.scratch_off);
+    unsigned char* smem_b = smem + L.b_off;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
-    uint64_t* full_bar = bars;                        // [stages]
-    uint64_t* empty_bar = bars + kTcMaxStages;        // [stages]
-    uint64_t* q_bar = bars + 2 * kTcMaxStages;        // [1]
-    uint64_t* acc_full = q_bar + 1;                   // [2]
-    uint64_t* acc_empty = acc_full + kTcAccStages;    // [2]
-    u64* s_thr_key = reinterpret_cast<u64*>(smem + L.state_off);           // [n_tile]
-    float* s_thr = reinterpret_cast<float*>(s_thr_key + p.n_tile);          // [n_tile]
-    int* s_count = reinterpret_cast<int*>(s_thr + p.n_tile);                // [n_tile]
-    int* s_lock = s_count + p.n_tile;                                       // [n_tile]
-    int* s_scratch_lock = s_lock + p.n_tile;                                // [1]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_scratch_lock + 1);     // [1]
+    uint64_t* full_bar = bars;                        // [stages]  used in the leader CTA
+    uint64_t* empty_bar = bars + kTcMaxStages;        // [stages]  per CTA (multicast commit)
+    uint64_t* q_full = bars + 2 * kTcMaxStages;       // [1]       leader
+    uint64_t* q_empty = q_full + 1;                   // [1]       per CTA (multicast commit)
+    uint64_t* acc_full = q_empty + 1;                 // [2]       per CTA (multicast commit)
+    uint64_t* acc_empty = acc_full + kTcAccStages;    // [2]       leader: 16 epilogue warps arrive
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + kTcAccStages);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
-    const int q0 = blockIdx.y * p.n_tile;             // first query of this CTA's block
-
-    // this CTA's tiles: first_tile, first_tile + stride, ... < tile_end
-    const int first_tile = blockIdx.x * p.tiles_per_slice;
-    int tile_end = first_tile + p.tiles_per_slice;
-    if (tile_end > p.num_tiles) tile_end = p.num_tiles;
-    const int my_tiles = first_tile < tile_end ? (tile_end - first_tile + p.tile_stride - 1) / p.tile_stride : 0;
-
-    uint32_t tmem_cols = 32;
-    while (tmem_cols < (uint32_t)(kTcAccStages * p.n_tile)) tmem_cols <<= 1;
+    const uint32_t rank = ptx::cluster_ctarank();     // 0 = leader
+    const int pair = blockIdx.x >> 1;
+    const int num_pairs = gridDim.x >> 1;
+    const int items_total = p.num_chunks * p.qblocks;
+    const bool reload_q = p.qblocks > 1;
 
     // ---- one-time setup ---------------------------------------------------------------------
     if (warp == 0 && lane == 0) {
@@ -116,132 +157,194 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
             ptx::mbar_init(&full_bar[i], 1);
             ptx::mbar_init(&empty_bar[i], 1);
         }
-        ptx::mbar_init(q_bar, 1);
+        ptx::mbar_init(q_full, 1);
+        ptx::mbar_init(q_empty, 1);
         for (int i = 0; i < kTcAccStages; ++i) {
             ptx::mbar_init(&acc_full[i], 1);
-            ptx::mbar_init(&acc_empty[i], 4);   // one arrive per epilogue warp
+            ptx::mbar_init(&acc_empty[i], 2 * kTcEpiWarps);
         }
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
-        ptx::tmem_alloc(s_tmem, tmem_cols);
-        ptx::tmem_relinquish();
+        ptx::tmem_alloc_pair(s_tmem, 512);
+        ptx::tmem_relinquish_pair();
     }
-    for (int j = tid; j < p.n_tile; j += kTcThreads) {
-        const ListRef st{&s_thr_key[j], &s_thr[j], &s_count[j], &s_lock[j]};
-        if (q0 + j < p.nq) list_init(st, p.seed_keys ? p.seed_keys[q0 + j] : 0ull);
-        else list_disable(st);
-    }
-    if (tid == 0) *s_scratch_lock = 0;
     ptx::tc_fence_before();
     __syncthreads();
+    ptx::cluster_sync_all();   // the peer's barriers exist before anything is signalled on them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
     if (warp == 0) {
-        // ================= TMA producer =================
+        // ================= TMA producer (both CTAs; bytes are counted on the leader's barriers) ====
         if (lane == 0) {
-            ptx::mbar_expect_tx(q_bar, (uint32_t)p.kblocks * p.n_tile * 128);
-            for (int kb = 0; kb < p.kblocks; ++kb)
-                ptx::tma_load_2d(smem_q + (size_t)kb * p.n_tile * 128, &map_queries, q_bar, kb * kTcKBlock, q0,
-                                 ptx::kEvictLast);
+            const uint32_t q_full_leader = ptx::mapa_u32(ptx::smem_u32(q_full), 0);
             int stage = 0;
             uint32_t phase = 0;
-            for (int i = 0; i < my_tiles; ++i) {
-                const int tile = first_tile + i * p.tile_stride;
-                for (int kb = 0; kb < p.kblocks; ++kb) {
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    ptx::mbar_expect_tx(&full_bar[stage], kTcStageBytes);
-                    ptx::tma_load_2d(smem_a + (size_t)stage * kTcStageBytes, &map_corpus, &full_bar[stage],
-                                     kb * kTcKBlock, tile * kTcTileRows, ptx::kEvictFirst);
-                    if (++stage == p.stages) {
-                        stage = 0;
-                        phase ^= 1;
+            uint32_t q_loads = 0;
+            for (int item = pair; item < items_total; item += num_pairs) {
+                const int chunk = item / p.qblocks;
+                const int qb = item - chunk * p.qblocks;
+                if (reload_q || q_loads == 0) {
+                    ptx::mbar_wait(q_empty, (q_loads & 1u) ^ 1u);   // MMAs that read the old block are done
+                    if (rank == 0) ptx::mbar_expect_tx(q_full, 2u * (uint32_t)p.kblocks * kTcQBlockBytes);
+                    for (int kb = 0; kb < p.kblocks; ++kb)
+                        ptx::tma_load_2d_pair(smem_q + (size_t)kb * kTcQBlockBytes, &map_queries, q_full_leader,
+                                              kb * kTcKBlock, qb * kTcQueriesPerPair + (int)rank * kTcQueriesPerCta,
+                                              ptx::kEvictLast);
+                    ++q_loads;
+                }
+                const int t0 = chunk * p.chunk_tiles;
+                const int t1 = min(t0 + p.chunk_tiles, p.tiles_total);
+                for (int t = t0; t < t1; ++t) {
+                    const int row0 = t * p.tile_mul * kTcTileRows + (int)rank * kTcRowsPerCta;
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2u * kTcStageBytes);
+                        ptx::tma_load_2d_pair(smem_b + (size_t)stage * kTcStageBytes, &map_corpus,
+                                              ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0), kb * kTcKBlock, row0,
+                                              p.policy);
+                        if (++stage == p.stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
                     }
                 }
             }
+            // the leader's last multicast commit (q_empty) must have landed here before this CTA may exit
+            if (reload_q && q_loads > 0) ptx::mbar_wait(q_empty, (q_loads & 1u) ^ 1u);
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = ptx::idesc_bf16_f32(kTcTileRows, (uint32_t)p.n_tile);
-            ptx::mbar_wait(q_bar, 0);
+        // ================= MMA issuer (leader CTA, one lane) =================
+        if (rank == 0 && lane == 0) {
+            const uint32_t idesc = ptx::idesc_bf16_f32(kTcQueriesPerPair, kTcTileRows);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int i = 0; i < my_tiles; ++i) {
-                ptx::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
-                ptx::tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.n_tile);
-                for (int kb = 0; kb < p.kblocks; ++kb) {
-                    ptx::mbar_wait(&full_bar[stage], phase);
+            uint32_t q_loads = 0;
+            for (int item = pair; item < items_total; item += num_pairs) {
+                const int chunk = item / p.qblocks;
+                if (reload_q || q_loads == 0) {
+                    ptx::mbar_wait(q_full, q_loads & 1u);
                     ptx::tc_fence_after();
-                    const uint64_t da = ptx::smem_desc_sw128(ptx::smem_u32(smem_a + (size_t)stage * kTcStageBytes));
-                    const uint64_t db = ptx::smem_desc_sw128(ptx::smem_u32(smem_q + (size_t)kb * p.n_tile * 128));
+                    ++q_loads;
+                }
+                const int t0 = chunk * p.chunk_tiles;
+                const int t1 = min(t0 + p.chunk_tiles, p.tiles_total);
+                for (int t = t0; t < t1; ++t) {
+                    ptx::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+                    ptx::tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kTcTileRows);
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        ptx::mbar_wait(&full_bar[stage], phase);
+                        ptx::tc_fence_after();
+                        const uint64_t da = ptx::smem_desc_sw128(ptx::smem_u32(smem_q + (size_t)kb * kTcQBlockBytes));
+                        const uint64_t db = ptx::smem_desc_sw128(ptx::smem_u32(smem_b + (size_t)stage * kTcStageBytes));
 #pragma unroll
-                    for (int kk = 0; kk < kTcKBlock / 16; ++kk) {
-                        // advance 16 elements = 32 bytes inside the 128-byte swizzle row: +2 (16-byte units)
-                        ptx::umma_bf16(tmem_d, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc,
-                                       (uint32_t)((kb | kk) != 0));
+                        for (int kk = 0; kk < kTcKBlock / 16; ++kk) {
+                            // advance 16 elements = 32 bytes inside the 128-byte swizzle row: +2 (16-byte units)
+                            ptx::umma_bf16_pair(tmem_d, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc,
+                                                (uint32_t)((kb | kk) != 0));
+                        }
+                        ptx::umma_commit_pair(&empty_bar[stage]);   // frees the stage in both CTAs
+                        if (++stage == p.stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
                     }
-                    ptx::umma_commit(&empty_bar[stage]);   // frees the smem stage when these MMAs retire
-                    if (++stage == p.stages) {
-                        stage = 0;
-                        phase ^= 1;
+                    ptx::umma_commit_pair(&acc_full[acc]);          // accumulator tile complete (both CTAs)
+                    if (++acc == kTcAccStages) {
+                        acc = 0;
+                        acc_phase ^= 1;
                     }
                 }
-                ptx::umma_commit(&acc_full[acc]);          // accumulator tile complete
+                if (reload_q) ptx::umma_commit_pair(q_empty);       // the query block may be overwritten
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue: one thread <-> one query =================
+        const int qt = warp & 3;                  // TMEM lane quarter this warp may read
+        const int half = (warp - 4) >> 2;         // column half of the accumulator
+        const uint32_t lane_addr = (uint32_t)(qt * 32) << 16;
+        const uint32_t acc_empty_leader0 = ptx::mapa_u32(ptx::smem_u32(&acc_empty[0]), 0);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int item = pair; item < items_total; item += num_pairs) {
+            const int chunk = item / p.qblocks;
+            const int qb = item - chunk * p.qblocks;
+            const int q = qb * kTcQueriesPerPair + (int)rank * kTcQueriesPerCta + qt * 32 + lane;
+            const size_t list_id = (size_t)(pair * 2 + half) * p.nq_pad + q;
+            // list state of (this pair, this column half, query q)
+            u64* my_list = nullptr;
+            u64 tk = 0ull;
+            float thr = -INFINITY;
+            int cnt = 0;
+            if constexpr (!PREPASS) {
+                my_list = p.lists + list_id * p.cap;
+                cnt = p.counts[list_id];
+                tk = p.thr_keys[list_id];
+                if (tk == 0ull && p.seed_keys != nullptr) tk = p.seed_keys[q];
+                if (tk != 0ull) thr = key_score(tk);
+                if (q >= p.nq) {   // padding query: nothing passes
+                    thr = INFINITY;
+                    tk = ~0ull;
+                }
+            }
+            const int t0 = chunk * p.chunk_tiles;
+            const int t1 = min(t0 + p.chunk_tiles, p.tiles_total);
+            for (int t = t0; t < t1; ++t) {
+                ptx::mbar_wait(&acc_full[acc], acc_phase);
+                ptx::tc_fence_after();
+                const uint32_t col0 = (uint32_t)(acc * kTcTileRows + half * 128);
+                const uint32_t row_base = (uint32_t)(t * p.tile_mul) * kTcTileRows + (uint32_t)half * 128u;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    float v[32];
+                    ptx::tmem_ld_32x32(tmem_base + lane_addr + col0 + (uint32_t)(c * 32), v);
+                    if constexpr (PREPASS) {
+                        float m = v[0];
+#pragma unroll
+                        for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+                        p.gmax[(size_t)q * p.groups + (size_t)t * kTcGroupsPerTile + half * 4 + c] = m;
+                    } else {
+                        bool any = false;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) any = any || (v[j] >= thr);
+                        if (any) {   // rare, per lane
+                            const uint32_t row_c = row_base + (uint32_t)(c * 32);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (v[j] >= thr) {
+                                    const uint32_t row = row_c + (uint32_t)j;
+                                    const u64 key = make_key(v[j], row);
+                                    if (key > tk && row < p.n_rows) {
+                                        my_list[cnt++] = key;
+                                        if (cnt == p.cap) {
+                                            tk = list_keep_top_k(my_list, cnt, p.k);
+                                            thr = key_score(tk);
+                                            cnt = p.k;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_cluster(acc_empty_leader0 + (uint32_t)(acc * 8));
                 if (++acc == kTcAccStages) {
                     acc = 0;
                     acc_phase ^= 1;
                 }
             }
-        }
-    } else if (warp >= 4) {
-        // ================= epilogue: threshold filter + candidate lists =================
-        const int ew = warp - 4;                           // TMEM lane quarter this warp may read
-        u64* my_lists = p.lists + ((size_t)blockIdx.x * p.nq_pad + q0) * p.cap;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int i = 0; i < my_tiles; ++i) {
-            const int tile = first_tile + i * p.tile_stride;
-            const long long row = (long long)tile * kTcTileRows + ew * 32 + lane;
-            const bool row_ok = row < p.n_rows;
-            ptx::mbar_wait(&acc_full[acc], acc_phase);
-            ptx::tc_fence_after();
-            for (int c = 0; c < p.n_tile; c += 32) {
-                float v[32];
-                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.n_tile + c), v);
-                unsigned passmask = 0;
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 t = ptx::lds_volatile_f4(&s_thr[c + 4 * j4]);
-                    passmask |= (v[4 * j4 + 0] >= t.x ? 1u : 0u) << (4 * j4 + 0);
-                    passmask |= (v[4 * j4 + 1] >= t.y ? 1u : 0u) << (4 * j4 + 1);
-                    passmask |= (v[4 * j4 + 2] >= t.z ? 1u : 0u) << (4 * j4 + 2);
-                    passmask |= (v[4 * j4 + 3] >= t.w ? 1u : 0u) << (4 * j4 + 3);
+            if constexpr (!PREPASS) {
+                if (q < p.nq) {
+                    p.counts[list_id] = cnt;
+                    p.thr_keys[list_id] = tk;
                 }
-                if (!row_ok) passmask = 0;
-                if (__any_sync(0xffffffffu, passmask != 0)) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const bool pj = (passmask >> j) & 1u;
-                        if (__any_sync(0xffffffffu, pj)) {
-                            const int q = c + j;
-                            const ListRef st{&s_thr_key[q], &s_thr[q], &s_count[q], &s_lock[q]};
-                            list_append_warp(st, my_lists + (size_t)q * p.cap, p.cap, p.k, pj,
-                                             make_key(v[j], (uint32_t)row), lane, scratch, s_scratch_lock);
-                        }
-                    }
-                }
-            }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
-            if (++acc == kTcAccStages) {
-                acc = 0;
-                acc_phase ^= 1;
             }
         }
     }
@@ -249,12 +352,58 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
     // ---- teardown ---------------------------------------------------------------------------
     ptx::tc_fence_before();
     __syncthreads();
-    for (int j = tid; j < p.n_tile; j += kTcThreads)
-        p.counts[(size_t)blockIdx.x * p.nq_pad + q0 + j] = (q0 + j < p.nq) ? s_count[j] : 0;
+    ptx::cluster_sync_all();   // the peer no longer reads this CTA's shared memory / TMEM / barriers
     if (warp == 2) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, tmem_cols);
+        ptx::tmem_dealloc_pair(tmem_base, 512);
     }
+}
+
+// k-th largest of each query's group maxima -> the seed threshold of the main pass.
+// gmax [nq_pad, groups]; out seed_keys[q]: a candidate must have key > seed (0 = no threshold).
+// One CTA per query: MSB-first 8-bit radix select on the order-preserving integer image.
+constexpr int kSeedThreads = 256;
+__global__ void __launch_bounds__(kSeedThreads) seed_select_kernel(const float* __restrict__ gmax, int groups, int k,
+                                                                   u64* __restrict__ seed_keys) {
+    __shared__ int hist[256];
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_rem;
+    const int q = blockIdx.x;
+    const int tid = threadIdx.x;
+    const float* g = gmax + (size_t)q * groups;
+    if (groups < k) {
+        if (tid == 0) seed_keys[q] = 0ull;
+        return;
+    }
+    if (tid == 0) {
+        s_prefix = 0u;
+        s_rem = k;
+    }
+    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        hist[tid] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
+        for (int i = tid; i < groups; i += kSeedThreads) {
+            const uint32_t o = score_to_ord(g[i]);
+            const bool in = pass == 0 || (o >> (shift + 8)) == (prefix >> (shift + 8));
+            if (in) atomicAdd(&hist[(o >> shift) & 255u], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int rem = s_rem, b = 255;
+            for (; b > 0; --b) {
+                if (hist[b] >= rem) break;
+                rem -= hist[b];
+            }
+            s_prefix = prefix | ((uint32_t)b << shift);
+            s_rem = rem;
+        }
+        __syncthreads();
+    }
+    // s_prefix = ord of the k-th largest maximum T; every score >= T must pass: key > (ord << 32) - 1
+    if (tid == 0) seed_keys[q] = s_prefix ? (((u64)s_prefix << 32) - 1ull) : 0ull;
 }
 
 // Host-side state of the tensor path kept in the index handle.
@@ -270,6 +419,7 @@ struct TensorPathState {
     bool attr_set = false;
 };
 
-inline bool tensor_path_supported(int dim) { return dim % kTcKBlock == 0 && dim >= 64 && dim <= 1024; }
+// dims whose resident query block (dim * 256 bytes per CTA) leaves room for >= 4 pipeline stages
+inline bool tensor_path_supported(int dim) { return dim % kTcKBlock == 0 && dim >= 64 && dim <= 512; }
 
 }  // namespace b2s

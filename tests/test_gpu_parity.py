@@ -292,8 +292,8 @@ def test_golden_vectors_tensor_path(pkg, oracle, golden_cases):
         idx.close()
 
 
-@pytest.mark.parametrize("n", [1, 127, 128, 129, 1000, 20000])
-@pytest.mark.parametrize("nq", [1, 5, 31, 32, 33, 64, 100, 129, 300])
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 255, 256, 257, 1000, 20000])
+@pytest.mark.parametrize("nq", [1, 5, 31, 32, 33, 64, 100, 129, 256, 257, 300, 600])
 def test_ragged_sizes_tensor(pkg, oracle, n, nq):
     X, Q = unit_rows(n, 384, n + 7), unit_rows(nq, 384, 2000 + nq)
     idx = build(pkg, X, path=2)
@@ -329,6 +329,39 @@ def test_tensor_ties_and_adversarial(pkg, oracle):
     idx = build(pkg, Xa, path=2)
     for k in (10, 100):
         check(oracle, idx, Xa, Qa, k, q_bf16=True)
+    idx.close()
+
+
+@pytest.mark.parametrize("k", [10, 100])
+def test_tensor_many_query_blocks(pkg, oracle, k):
+    """Several 256-query blocks share every corpus chunk (work items = chunk x query block), with
+    small chunks so that each CTA pair switches query blocks many times."""
+    X, Q = unit_rows(150000, 384, 31), unit_rows(700, 384, 32)
+    for chunk in (0, 3):
+        idx = build(pkg, X, path=2)
+        if chunk:
+            idx.set_option("tc_chunk_tiles", chunk)
+        check(oracle, idx, X, Q, k, q_bf16=True)
+        st = idx.stats()
+        assert st["path"] == 2 and st["seeded"] == 1 and st["passes"] == 3, st
+        idx.close()
+
+
+def test_tensor_more_queries_than_one_round(pkg, oracle):
+    """nq above the 4096-query workspace round."""
+    X, Q = unit_rows(5000, 384, 41), unit_rows(4200, 384, 42)
+    idx = build(pkg, X, path=2)
+    check(oracle, idx, X, Q, 10, q_bf16=True)
+    idx.close()
+
+
+def test_tensor_list_overflow_without_seed(pkg, oracle):
+    """No sampled thresholds: every thread-private list fills and is compacted repeatedly."""
+    X, Q = unit_rows(60000, 384, 51), unit_rows(50, 384, 52)
+    idx = build(pkg, X, path=2, seed=0)
+    for k in (1, 10, 64, 300):
+        check(oracle, idx, X, Q, k, q_bf16=True)
+        assert idx.stats()["seeded"] == 0
     idx.close()
 
 
