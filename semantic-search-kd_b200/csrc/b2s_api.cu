@@ -101,7 +101,7 @@ struct b2s_index {
     int opt_rescore_pad = 32;
     int opt_timing = 0;
     int opt_tc_min_nq = 3;
-    int opt_tc_sample_div = 64;   // the threshold pre-pass samples 1 / this of the full tiles
+    int opt_tc_sample_div = 0;    // the threshold pre-pass samples 1 / this of the full tiles (0 = by k)
     int opt_tc_chunk_lo = 48;     // tiles per work item when several query blocks share the corpus
     int opt_tc_chunk_hi = 96;
     // workspace
@@ -601,7 +601,7 @@ B2S_API int b2s_set_option(b2s_index* idx, const char* name, int64_t value) {
     } else if (s == "tc_min_nq") {
         idx->opt_tc_min_nq = (int)std::max<int64_t>(1, value);
     } else if (s == "tc_sample_div") {
-        idx->opt_tc_sample_div = (int)std::min<int64_t>(1 << 20, std::max<int64_t>(1, value));
+        idx->opt_tc_sample_div = (int)std::min<int64_t>(1 << 20, std::max<int64_t>(0, value));
     } else if (s == "tc_chunk_tiles") {
         if (value < 1 || value > 4096) return fail(B2S_ERR_INVALID, "tc_chunk_tiles must be in [1, 4096]");
         idx->opt_tc_chunk_lo = idx->opt_tc_chunk_hi = (int)value;

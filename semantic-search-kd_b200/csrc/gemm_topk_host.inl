@@ -84,8 +84,12 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
     // threshold pre-pass: a sample of full tiles whose 32-row group maxima bound the k-th best score
     int sample_tiles = 0, sample_stride = 1;
     if (seed && tiles_full > 0) {
+        // Sample density by k (measured at 1024 queries x 8.8M rows, sweep in profiles/): the pre-pass costs
+        // 1/div of a main pass, the survivors that take the epilogue's slow path number ~ k * div.
+        const int div = idx->opt_tc_sample_div > 0 ? idx->opt_tc_sample_div
+                                                   : (k <= 25 ? 64 : (k <= 50 ? 32 : (k <= 150 ? 16 : 8)));
         const int want_groups = std::max(1024, 8 * k);
-        int ts = std::max((tiles_full + idx->opt_tc_sample_div - 1) / idx->opt_tc_sample_div,
+        int ts = std::max((tiles_full + div - 1) / div,
                           (want_groups + kTcGroupsPerTile - 1) / kTcGroupsPerTile);
         ts = std::min(ts, tiles_full);
         sample_stride = std::max(1, tiles_full / ts);

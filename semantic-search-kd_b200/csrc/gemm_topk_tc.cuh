@@ -308,22 +308,34 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
                         for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
                         p.gmax[(size_t)q * p.groups + (size_t)t * kTcGroupsPerTile + half * 4 + c] = m;
                     } else {
-                        bool any = false;
+                        // group maxima first: one compare per 8 rows on the hot path, and the
+                        // (rare, per-lane) slow path only walks the groups that hold a survivor
+                        float g8[4];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) any = any || (v[j] >= thr);
-                        if (any) {   // rare, per lane
+                        for (int g = 0; g < 4; ++g) {
+                            float m = fmaxf(fmaxf(v[8 * g], v[8 * g + 1]), v[8 * g + 2]);
+                            m = fmaxf(fmaxf(m, v[8 * g + 3]), v[8 * g + 4]);
+                            m = fmaxf(fmaxf(m, v[8 * g + 5]), v[8 * g + 6]);
+                            g8[g] = fmaxf(m, v[8 * g + 7]);
+                        }
+                        if (fmaxf(fmaxf(g8[0], g8[1]), fmaxf(g8[2], g8[3])) >= thr) {
                             const uint32_t row_c = row_base + (uint32_t)(c * 32);
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                if (v[j] >= thr) {
-                                    const uint32_t row = row_c + (uint32_t)j;
-                                    const u64 key = make_key(v[j], row);
-                                    if (key > tk && row < p.n_rows) {
-                                        my_list[cnt++] = key;
-                                        if (cnt == p.cap) {
-                                            tk = list_keep_top_k(my_list, cnt, p.k);
-                                            thr = key_score(tk);
-                                            cnt = p.k;
+                            for (int g = 0; g < 4; ++g) {
+                                if (g8[g] >= thr) {
+#pragma unroll
+                                    for (int j = 8 * g; j < 8 * g + 8; ++j) {
+                                        if (v[j] >= thr) {
+                                            const uint32_t row = row_c + (uint32_t)j;
+                                            const u64 key = make_key(v[j], row);
+                                            if (key > tk && row < p.n_rows) {
+                                                my_list[cnt++] = key;
+                                                if (cnt == p.cap) {
+                                                    tk = list_keep_top_k(my_list, cnt, p.k);
+                                                    thr = key_score(tk);
+                                                    cnt = p.k;
+                                                }
+                                            }
                                         }
                                     }
                                 }

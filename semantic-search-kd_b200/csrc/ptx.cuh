@@ -161,7 +161,10 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default semantics (release at CTA scope), as CUTLASS' ClusterBarrier::arrive(cta_id): the data
+    // hand-over is TMEM -> registers, ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync;
+    // a cluster-scope release would add a full memory barrier per tile for nothing.
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into THIS CTA's shared memory whose bytes are counted on the barrier at `bar_cluster_addr`
 // (the leader's), as the 2-CTA MMA consumes both halves together.

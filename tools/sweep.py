@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--seed", type=int, default=-1)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--out", type=str, default="")
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (repeatable)")
     args = ap.parse_args()
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     bw = peaks.get("hbm_gbs", 6650.0) * 1e9
@@ -34,6 +35,9 @@ def main():
     idx = pkg.FlatIPIndex(DIM, metric="inner_product", device=0)
     idx.set_option("path", args.path)
     idx.set_option("seed", args.seed)
+    for o in args.opt:
+        name, val = o.split("=")
+        idx.set_option(name, int(val))
     idx.reserve(args.rows)
     for blk in make_rows(torch, 0, args.rows, dev):
         idx.add(blk)
