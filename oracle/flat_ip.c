@@ -12,12 +12,19 @@
  *   - output convention:      src/serve/app.py:299-301  ([nq,k], id -1 = none)
  *   - ANCE margin filter:     src/mining/miners.py:237-247
  *
- * PARITY UNPINNED: the arithmetic of the reference lives in the third-party
- * dependency faiss-cpu ^1.7.4 (pyproject.toml:15), which is neither vendored
- * under /root/reference nor installable here, and no reference test pins a
- * retrieved id or score.  This file restates faiss' published IndexFlatIP
- * semantics: score = sum_i q_i * x_i, the k largest scores per query returned
- * in descending order, int64 labels, unfilled slots = (-FLT_MAX, -1), a later
+ * PINNING: the oracle is pinned against outputs of the reference's own exact
+ * search code RUN in the build container -- KDEvaluator.evaluate_retrieval
+ * (src/kd/eval.py:42-101), scripts/simple_eval.py:evaluate_model and
+ * ANCEMiner.mine (src/mining/miners.py:184-253), imported unmodified with the
+ * absent model stubbed; generator tests/golden/make_ref_golden.py, fixtures
+ * tests/golden/ref_eval.npz + ref_ance.json, checked by
+ * tests/test_reference_golden.py.  What stays UNPINNED is faiss itself: the
+ * serving path's arithmetic lives in the third-party dependency faiss-cpu
+ * ^1.7.4 (pyproject.toml:15), neither vendored under /root/reference nor
+ * installable here, and no reference test pins a retrieved id or score.  For
+ * that half this file restates faiss' published IndexFlatIP semantics:
+ * score = sum_i q_i * x_i, the k largest scores per query returned in
+ * descending order, int64 labels, unfilled slots = (-FLT_MAX, -1), a later
  * row never displaces an earlier row of equal score (strict '>' replacement).
  * Ties in the OUTPUT are ordered by ascending id (deterministic refinement).
  *

@@ -10,12 +10,17 @@ CPU oracle for the exact inner-product top-k path.  Two restatements:
 * ``flat_ip_topk``     -- ctypes binding of ``oracle/flat_ip.c`` (same
   semantics, OpenMP, streams over corpus blocks) for sizes numpy cannot hold.
 
-PARITY UNPINNED: faiss-cpu (``pyproject.toml:15``, ``^1.7.4``) is neither in
-``/root/reference`` nor installable, and no reference test pins a retrieved id
-or score; see ``flat_ip.c`` for the semantics restated.  The golden vectors
-under ``tests/golden/`` are produced by ``tests/golden/make_golden.py`` from the
-numpy restatement on the reference's own fixture recipe
-(``tests/conftest.py:65-73``: ``np.random.seed(42); randn(10,384)``; unit-norm).
+PINNING: pinned against outputs of the reference's own exact-search code run in
+the build container (``tests/golden/make_ref_golden.py`` imports
+``src/kd/eval.py``, ``scripts/simple_eval.py`` and ``src/mining/miners.py``
+unmodified from ``/root/reference`` with the absent model stubbed; fixtures
+``tests/golden/ref_eval.npz``, ``ref_ance.json``; test
+``tests/test_reference_golden.py``).  faiss-cpu itself (``pyproject.toml:15``,
+``^1.7.4``) is neither in ``/root/reference`` nor installable, and no reference
+test pins a retrieved id or score, so the faiss half (tie order, -1 padding)
+follows faiss' published semantics, see ``flat_ip.c``.  The older vectors under
+``tests/golden/`` (``make_golden.py``) come from the numpy restatement on the
+reference's fixture recipe (``tests/conftest.py:65-73``).
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU legs import
 this module.  The product package never does.
