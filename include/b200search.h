@@ -156,6 +156,30 @@ B2S_API int b2s_read_rows_f32(b2s_index* idx, int64_t start, int64_t n, float* o
 /* Device pointer of the bf16 corpus [ntotal, dim] (borrowed; valid until the next add). */
 B2S_API const void* b2s_rows_device(const b2s_index* idx);
 
+/*
+ * Inner products of each query with chosen corpus rows: out[q, j] = <queries[q], row ids[q, j]>
+ * (ids are global, i.e. include the id offset; ids outside this shard give -FLT_MAX).  DEVICE
+ * buffers.  round_q_bf16 != 0 rounds the query to bf16 first (the tensor path's operand type).
+ * Used to score a query's known positives for the ANCE margin
+ * (src/mining/miners.py:228-236: pos_scores = compute_similarity(q, pos_embs); max()).
+ */
+B2S_API int b2s_score_rows_device(b2s_index* idx, const void* queries, int q_dtype, int round_q_bf16,
+                                  int64_t nq, const int64_t* ids, int m, float* out_scores,
+                                  void* cuda_stream);
+
+/*
+ * Replaces the selection loop of ANCEMiner.mine (src/mining/miners.py:237-247) for corpus-wide
+ * candidates: per query keep, in order, the first top_k of its k_in sorted candidates
+ * (cand_scores descending, cand_ids; -1 padded) that are not among its positives
+ * (pos_ids [nq, n_pos], -1 padded) and whose score >= max(pos_scores) - margin (0.0 - margin when
+ * a query has no positive).  DEVICE buffers; out_ids / out_scores [nq, top_k] padded with
+ * (-1, -FLT_MAX); out_counts [nq] optional.
+ */
+B2S_API int b2s_ance_filter_device(int device, const float* cand_scores, const int64_t* cand_ids,
+                                   int64_t nq, int k_in, const int64_t* pos_ids, const float* pos_scores,
+                                   int n_pos, float margin, int top_k, int64_t* out_ids,
+                                   float* out_scores, int32_t* out_counts, void* cuda_stream);
+
 B2S_API int b2s_last_stats(const b2s_index* idx, b2s_stats* out);
 
 /*

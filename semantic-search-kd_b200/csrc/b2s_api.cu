@@ -17,6 +17,7 @@
 #include <string>
 
 #include "../../include/b200search.h"
+#include "ance_filter.cuh"
 #include "merge_topk.cuh"
 #include "scan_topk.cuh"
 #include "select.cuh"
@@ -816,6 +817,47 @@ B2S_API int64_t b2s_packed_bytes(int64_t nq, int k) {
 }
 
 B2S_API const void* b2s_rows_device(const b2s_index* idx) { return idx ? idx->rows : nullptr; }
+
+B2S_API int b2s_score_rows_device(b2s_index* idx, const void* queries, int q_dtype, int round_q_bf16, int64_t nq,
+                                  const int64_t* ids, int m, float* out_scores, void* cuda_stream) {
+    if (!idx) return fail(B2S_ERR_INVALID, "null index");
+    if (nq < 0 || m < 0) return fail(B2S_ERR_INVALID, "nq and m must be >= 0");
+    if (nq == 0 || m == 0) return B2S_OK;
+    if (!queries || !ids || !out_scores) return fail(B2S_ERR_INVALID, "null buffer");
+    if (q_dtype != B2S_DTYPE_F32 && q_dtype != B2S_DTYPE_BF16) return fail(B2S_ERR_INVALID, "bad q_dtype");
+    if (idx->metric == B2S_METRIC_COSINE)
+        return fail(B2S_ERR_UNSUPPORTED, "b2s_score_rows_device expects pre-normalised queries: use an inner-product index");
+    std::lock_guard<std::mutex> g(idx->mu);
+    int rc = use_device(idx);
+    if (rc != B2S_OK) return rc;
+    const long long pairs = (long long)nq * m;
+    const int warps = 8;
+    score_rows_kernel<<<(unsigned)((pairs + warps - 1) / warps), warps * 32, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
+        idx->rows, idx->n, idx->dim, queries, q_dtype == B2S_DTYPE_BF16, round_q_bf16 ? 1 : 0, nq, m,
+        reinterpret_cast<const long long*>(ids), idx->id_offset, out_scores);
+    CUDA_TRY(cudaGetLastError());
+    return B2S_OK;
+}
+
+B2S_API int b2s_ance_filter_device(int device, const float* cand_scores, const int64_t* cand_ids, int64_t nq, int k_in,
+                                   const int64_t* pos_ids, const float* pos_scores, int n_pos, float margin, int top_k,
+                                   int64_t* out_ids, float* out_scores, int32_t* out_counts, void* cuda_stream) {
+    if (nq < 0 || k_in < 0 || n_pos < 0 || top_k < 0) return fail(B2S_ERR_INVALID, "bad arguments");
+    if (nq == 0 || top_k == 0) return B2S_OK;
+    if (!out_ids || !out_scores || (k_in > 0 && (!cand_scores || !cand_ids)) || (n_pos > 0 && (!pos_ids || !pos_scores)))
+        return fail(B2S_ERR_INVALID, "null buffer");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(B2S_ERR_NO_DEVICE, "no CUDA device: libb200search has no CPU fallback");
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    ance_filter_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
+        cand_scores, reinterpret_cast<const long long*>(cand_ids), k_in, reinterpret_cast<const long long*>(pos_ids),
+        pos_scores, n_pos, margin, top_k, nq, reinterpret_cast<long long*>(out_ids), out_scores, out_counts);
+    CUDA_TRY(cudaGetLastError());
+    return B2S_OK;
+}
 
 B2S_API int b2s_last_stats(const b2s_index* idx, b2s_stats* out) {
     if (!idx || !out) return fail(B2S_ERR_INVALID, "bad arguments");

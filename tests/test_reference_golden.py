@@ -39,10 +39,14 @@ def assert_same_retrieval(I, ref_ids, X, Q, tol, what):
         s_ref = np.array([Qd[i] @ Xd[j] for j in ref_ids[i]])
         s_our = np.array([Qd[i] @ Xd[j] for j in I[i]])
         np.testing.assert_allclose(s_our, s_ref, rtol=0, atol=tol, err_msg=f"{what} row {i}")
-        if len(np.unique(s_ref)) == len(s_ref) and tol == 0:
+        gaps = np.abs(np.diff(np.sort(s_ref))) if len(s_ref) > 1 else np.array([np.inf])
+        if gaps.min() > 2 * tol:   # no (near-)tie in this row: the ids themselves must be identical
             assert np.array_equal(I[i], ref_ids[i]), (what, i, I[i], ref_ids[i])
-        elif len(np.unique(np.round(s_ref / max(tol, 1e-12)))) == len(s_ref):
-            assert np.array_equal(I[i], ref_ids[i]), (what, i, I[i], ref_ids[i])
+        else:
+            # (near-)ties may swap; every id must still be one the reference could have returned
+            kth = s_ref[-1]
+            for j, s in zip(I[i], s_our):
+                assert j in ref_ids[i] or abs(s - kth) <= max(tol, 1e-12), (what, i, j, s, kth)
 
 
 def test_oracle_retrieves_what_the_reference_retrieved(oracle, ref_case):
@@ -82,6 +86,82 @@ def test_cuda_path_retrieves_what_the_reference_retrieved(ref_case):
             k = int(key.split("_k")[1])
             D, I = idx.search(Q, k)
             assert idx.stats()["path"] == path
-            # bf16 storage: ids may swap only between scores closer than the north-star tolerance
-            assert_same_retrieval(I, z[key], X, Q, 1e-3, f"{key} path {path}")
+            # north-star parity rule against the ids the REFERENCE retrieved: an id only one side
+            # returned must score within 1e-3 of the k-th score (bf16 storage may swap near-ties)
+            ref_ids = z[key]
+            ref_scores = np.array([[Q[i].astype(np.float64) @ X[j].astype(np.float64) for j in ref_ids[i]]
+                                   for i in range(len(Q))], dtype=np.float32)
+            from oracle import oracle as orc
+            rep = orc.compare_topk(D, I, ref_scores, ref_ids, X, Q, tie_tol=1e-3)
+            assert rep["ok"] and rep["max_abs_score_err"] <= 1e-3, (key, path, rep)
+            assert rep["set_match"] >= len(Q) // 2, (key, path, rep)   # swaps only where the k-th score is a near-tie
         idx.close()
+
+
+@pytest.mark.gpu
+def test_cuda_ance_miner_matches_reference(ref_case):
+    """ANCEMiner.mine mirror (similarity on the GPU through b2s_similarity) returns exactly the hard
+    negatives the reference's ANCEMiner.mine returned on the same stubbed model."""
+    import make_ref_golden as mr
+    import semantic_search_kd_b200 as pkg
+    X, Q, _, meta = ref_case
+    stub = mr.StubStudent(X, Q)
+    queries = [f"q{i}" for i in range(meta["nq"])]
+    texts = {f"d{i}": f"d{i}" for i in range(meta["n"])}
+    for name, ref_negs in meta["negatives"].items():
+        margin, top_k = float(name.split("_")[0][len("margin"):]), int(name.split("_top")[1])
+        got = pkg.ANCEMiner(stub, margin=margin).mine(queries, meta["positives"], meta["candidates"], texts, texts,
+                                                       top_k=top_k)
+        assert got == ref_negs, name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nq,top_k", [(40, 20), (300, 200)])
+def test_cuda_corpus_wide_ance(oracle, nq, top_k):
+    """mine_corpus = exact search + the reference's selection rule (miners.py:237-247) with the
+    query's positives removed, checked against the oracle restatement on the same data."""
+    import semantic_search_kd_b200 as pkg
+    from conftest import unit_rows
+    n, margin = 30000, 0.05
+    X, Q = unit_rows(n, 384, 61), unit_rows(nq, 384, 62)
+    Xb = oracle.round_bf16(X)
+    rng = np.random.default_rng(5)
+    D0, I0 = oracle.flat_ip_topk(Xb, Q, 4)
+    positives = []
+    for i in range(nq):
+        p = [int(I0[i, 1])] if i % 3 else []                      # a strong positive (rank 2) or none
+        if i % 5 == 0:
+            p.append(int(rng.integers(0, n)))                     # plus a random (weak) one
+        positives.append(p)
+    idx = pkg.FlatIPIndex(384, metric="inner_product")
+    idx.add(X)
+    ids, scores, counts = pkg.ANCEMiner(None, margin=margin).mine_corpus(idx, Q, positives, top_k=top_k)
+    path = idx.stats()["path"]
+    Qe = oracle.round_bf16(Q) if path == 2 else Q
+    n_pos = max(1, max(len(p) for p in positives))
+    Dr, Ir = oracle.flat_ip_topk(Xb, Qe, top_k + n_pos)
+    for i in range(nq):
+        ps = [float(Qe[i].astype(np.float64) @ Xb[p].astype(np.float64)) for p in positives[i]]
+        thr = (max(ps) if ps else 0.0) - margin
+        sure, maybe = [], set()
+        for s, d in zip(Dr[i], Ir[i]):
+            if d < 0 or int(d) in positives[i]:
+                continue
+            if s >= thr + 1e-4:
+                sure.append(int(d))
+            elif s >= thr - 1e-4:
+                maybe.add(int(d))
+        got = [int(x) for x in ids[i][:counts[i]]]
+        assert all(x == -1 for x in ids[i][counts[i]:])
+        assert not (set(got) & set(positives[i]))
+        exp = sure[:top_k]
+        if len(sure) >= top_k:
+            # ids may swap only between scores within fp32 summation noise of each other
+            assert set(got) - set(exp) <= set(sure) | maybe and len(got) == top_k, i
+            s_exp = [float(Qe[i].astype(np.float64) @ Xb[d].astype(np.float64)) for d in exp]
+            s_got = [float(Qe[i].astype(np.float64) @ Xb[d].astype(np.float64)) for d in got]
+            np.testing.assert_allclose(s_got, s_exp, atol=2e-5)
+        else:
+            assert set(exp) <= set(got) <= set(exp) | maybe, (i, got, exp, maybe)
+        assert np.all(np.diff(scores[i][:counts[i]]) <= 0)
+    idx.close()
