@@ -170,7 +170,8 @@ def run_reference(args):
 def workload_config(n_gpus):
     return {"workload": "BASELINE configs[1]: 8,841,823 x 384 bf16 corpus, batch-1 serving search, exact top-10",
             "rows": N_ROWS, "dim": DIM, "k": K, "batch": 1,
-            "parallelism": f"corpus row-sharded x{n_gpus}" + (", NCCL all-gather of k candidates + merge" if n_gpus > 1 else ""),
+            "parallelism": f"corpus row-sharded x{n_gpus}" + (", k candidates per query exchanged over NVLink peer memory "
+                                                              "inside the merge kernel" if n_gpus > 1 else ""),
             "l2": "inputs larger than L2: every step streams the whole bf16 shard "
                   f"({N_ROWS * DIM * 2 / n_gpus / 1e9:.2f} GB per GPU vs 126 MB L2); 1024 distinct queries cycled"}
 
@@ -252,7 +253,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
     if world > 1:
-        idx = ShardedFlatIPIndex(DIM, metric="inner_product", local_index=local)
+        idx = ShardedFlatIPIndex(DIM, metric="inner_product", local_index=local, exchange=args.exchange)
         idx.local.set_id_offset(lo)
         idx.n_total, idx.range = args.rows, (lo, hi)
     else:
@@ -292,7 +293,8 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     st = local.stats()
-    launches_per_step = st["kernel_launches"] + (1 if world > 1 else 0)
+    exchange = getattr(idx, "exchange", None) if world > 1 else None
+    launches_per_step = st["kernel_launches"] + (1 if exchange == "nccl" else 0)
     clk = clocks.stop() if rank == 0 else None
 
     # dominant-kernel (K1) durations recorded by the library inside the timed region
@@ -354,7 +356,7 @@ def run_ours(args):
                 "e2e": {"value": e2e_steps / e2e_s, "unit": "queries/s", "steps": e2e_steps,
                         "h2d_bytes_per_step": DIM * 4, "d2h_bytes_per_step": K * 12,
                         "api": "FlatIPIndex.search(np.ndarray, k) -> b2s_search (host buffers)" if world == 1
-                        else "ShardedFlatIPIndex.search(np.ndarray, k)"},
+                        else f"ShardedFlatIPIndex.search(np.ndarray, k) [exchange={exchange}]"},
                 "latency_ms": {"e2e_p50": float(np.percentile(lat, 50) * 1e3), "e2e_p99": float(np.percentile(lat, 99) * 1e3),
                                "device_p50": float(np.percentile(tot, 50)) if len(tot) else None,
                                "device_p99": float(np.percentile(tot, 99)) if len(tot) else None,
@@ -392,6 +394,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-hnsw", action="store_true")
     ap.add_argument("--no-batched", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="multi-GPU candidate exchange: fused peer-memory kernel (default) or NCCL all-gather")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

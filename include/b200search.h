@@ -180,6 +180,38 @@ B2S_API int b2s_ance_filter_device(int device, const float* cand_scores, const i
                                    int n_pos, float margin, int top_k, int64_t* out_ids,
                                    float* out_scores, int32_t* out_counts, void* cuda_stream);
 
+/*
+ * Row-sharded search with the candidate exchange fused into the merge kernel (no NCCL on the data
+ * path): every rank's merge CTA stores its local top-k straight into every peer's exchange buffer
+ * over NVLink (peer-mapped memory + a release flag per (rank, query)), waits for the peers' flags
+ * in its own memory and merges G*k candidates.  Realises the reference's "shard, fan out, merge"
+ * prose (docs/operations/scaling-and-performance.md:154-172) on one 8-GPU box.
+ *
+ *   b2s_exchange_create   allocate this rank's buffer (slot_bytes >= b2s_packed_bytes(nq, k) of the
+ *                         largest call, max_nq flags per rank); writes a 64-byte CUDA IPC handle
+ *   b2s_exchange_connect  handles = world * 64 bytes, every rank's handle in rank order (exchanged
+ *                         by the host over its own channel); raw_pointers != 0:
+ *                         handles is instead an array of `world` device pointers (ranks emulated
+ *                         inside one process: b2s_exchange_local of each)
+ *   b2s_search_sharded_device   like b2s_search_device, outputs are the GLOBAL top-k (ids include
+ *                         each shard's id offset).  All ranks must issue the same sequence of
+ *                         calls with the same (nq, k).  phase 0 = whole call; phase 1 = local
+ *                         search + push only and phase 2 = wait + merge only (lets a test run
+ *                         several emulated ranks one after the other on a single GPU).
+ *   b2s_exchange_status   0, or the sequence number of a call whose wait timed out (synchronises)
+ */
+B2S_API int b2s_exchange_create(b2s_index* idx, int world, int rank, int64_t slot_bytes, int max_nq,
+                                void* ipc_handle_out);
+B2S_API void* b2s_exchange_local(const b2s_index* idx);
+B2S_API int b2s_exchange_connect(b2s_index* idx, const void* handles, int raw_pointers);
+B2S_API int b2s_exchange_status(b2s_index* idx);
+B2S_API int b2s_search_sharded_device(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, int k,
+                                      float* out_scores, int64_t* out_ids, void* cuda_stream, int phase);
+/* HOST-buffer variant of the whole sharded call (phase 0): H2D + exchange + D2H inside; every rank
+ * gets the global top-k.  This is what ShardedFlatIPIndex.search(np.ndarray, k) calls. */
+B2S_API int b2s_search_sharded(b2s_index* idx, const float* queries, int64_t nq, int k, float* out_scores,
+                               int64_t* out_ids);
+
 B2S_API int b2s_last_stats(const b2s_index* idx, b2s_stats* out);
 
 /*

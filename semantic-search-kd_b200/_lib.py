@@ -17,7 +17,7 @@ _ROOT = _PKG.parent
 _CSRC = _PKG / "csrc"
 _SO = _PKG / "libb200search.so"
 _SOURCES = ["b2s_api.cu", "select.cuh", "scan_topk.cuh", "merge_topk.cuh", "util_kernels.cuh",
-            "gemm_topk_tc.cuh", "gemm_topk_host.inl", "ptx.cuh", "ance_filter.cuh"]
+            "gemm_topk_tc.cuh", "gemm_topk_host.inl", "ptx.cuh", "ance_filter.cuh", "exchange.cuh"]
 
 B2S_OK = 0
 B2S_ERR_INVALID = -1
@@ -38,6 +38,8 @@ EXPORTS = [
     "b2s_set_option", "b2s_get_option", "b2s_search", "b2s_search_device", "b2s_merge_device",
     "b2s_similarity", "b2s_read_rows_f32", "b2s_rows_device", "b2s_last_stats", "b2s_read_timings",
     "b2s_packed_bytes", "b2s_merge_packed_device", "b2s_score_rows_device", "b2s_ance_filter_device",
+    "b2s_exchange_create", "b2s_exchange_local", "b2s_exchange_connect", "b2s_exchange_status",
+    "b2s_search_sharded_device", "b2s_search_sharded",
 ]
 
 
@@ -133,6 +135,18 @@ def lib() -> ctypes.CDLL:
     L.b2s_score_rows_device.restype = i32
     L.b2s_ance_filter_device.argtypes = [i32, vp, vp, i64, i32, vp, vp, i32, ctypes.c_float, i32, vp, vp, vp, vp]
     L.b2s_ance_filter_device.restype = i32
+    L.b2s_exchange_create.argtypes = [vp, i32, i32, i64, i32, vp]
+    L.b2s_exchange_create.restype = i32
+    L.b2s_exchange_local.argtypes = [vp]
+    L.b2s_exchange_local.restype = vp
+    L.b2s_exchange_connect.argtypes = [vp, vp, i32]
+    L.b2s_exchange_connect.restype = i32
+    L.b2s_exchange_status.argtypes = [vp]
+    L.b2s_exchange_status.restype = i32
+    L.b2s_search_sharded_device.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp, i32]
+    L.b2s_search_sharded_device.restype = i32
+    L.b2s_search_sharded.argtypes = [vp, vp, i64, i32, vp, vp]
+    L.b2s_search_sharded.restype = i32
     for name in ("b2s_create", "b2s_destroy", "b2s_reserve", "b2s_add_f32", "b2s_add_bf16", "b2s_dim",
                  "b2s_reset", "b2s_set_id_offset", "b2s_set_option", "b2s_search", "b2s_search_device",
                  "b2s_merge_device", "b2s_similarity", "b2s_read_rows_f32", "b2s_last_stats"):

@@ -15,9 +15,11 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/b200search.h"
 #include "ance_filter.cuh"
+#include "exchange.cuh"
 #include "merge_topk.cuh"
 #include "scan_topk.cuh"
 #include "select.cuh"
@@ -118,6 +120,20 @@ struct b2s_index {
     bool ev_valid = false;
     b2s_stats stats;
     std::mutex mu;
+    // cross-GPU candidate exchange (exchange.cuh); ex_call != nullptr only inside a sharded search
+    struct Exchange {
+        unsigned char* local = nullptr;
+        size_t bytes = 0;
+        int world = 0, rank = 0, max_nq = 0;
+        long long slot_stride = 0, flags_off = 0;
+        unsigned char** peers_dev = nullptr;   // device array [world]
+        std::vector<void*> opened;             // cudaIpcOpenMemHandle'd peer mappings
+        unsigned* status = nullptr;            // device word
+        unsigned seq = 0;
+        bool connected = false;
+    } ex;
+    const ExchangeArgs* ex_call = nullptr;
+    int ex_fused = 0;
 #ifndef B2S_NO_TENSOR_PATH
     TensorPathState tc;
 #endif
@@ -210,9 +226,19 @@ bool dim_supported(int dim) {
     return dim == 128 || dim == 256 || dim == 384 || dim == 512 || dim == 768 || dim == 1024;
 }
 
-int launch_merge(const MergeParams& mp, int nq, cudaStream_t s) {
+// Final (or seeding) per-query merge of `nq` queries starting at query q_offset of the call.  Inside a
+// sharded search the final merge also pushes the local top-k to every rank (and, fused, waits and
+// merges the ranks' candidates): exchange.cuh.
+int launch_merge(const b2s_index* idx, const MergeParams& mp, int nq, int q_offset, cudaStream_t s) {
     if (mp.num_lists > kMergeMaxLists) return fail(B2S_ERR_UNSUPPORTED, "too many candidate lists per query");
-    merge_topk_kernel<<<nq, kMergeThreads, 0, s>>>(mp);
+    if (idx->ex_call != nullptr && mp.out_kth_key == nullptr) {
+        ExchangeArgs ex = *idx->ex_call;
+        ex.q_offset = q_offset;
+        if (idx->ex_fused) merge_exchange_kernel<true><<<nq, kMergeThreads, 0, s>>>(mp, ex);
+        else merge_exchange_kernel<false><<<nq, kMergeThreads, 0, s>>>(mp, ex);
+    } else {
+        merge_topk_kernel<<<nq, kMergeThreads, 0, s>>>(mp);
+    }
     CUDA_TRY(cudaGetLastError());
     return B2S_OK;
 }
@@ -277,7 +303,7 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
                 mp.out_ids = reinterpret_cast<long long*>(out_ids) + (size_t)c0 * k;
             }
             if (pass == 1 && idx->opt_timing && c0 == 0) cudaEventRecord(idx->ev[2], s);
-            if ((rc = launch_merge(mp, cn, s)) != B2S_OK) return rc;
+            if ((rc = launch_merge(idx, mp, cn, (int)c0, s)) != B2S_OK) return rc;
             idx->stats.kernel_launches++;
         }
     }
@@ -314,6 +340,24 @@ int search_impl(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, in
         idx->ev_valid = false;
     }
 
+    if (idx->n == 0 && idx->ex_call != nullptr) {
+        // empty shard of a sharded search: contribute "no candidates" for every query
+        MergeParams mp;
+        memset(&mp, 0, sizeof(mp));
+        mp.k = k;
+        mp.cap = 64;
+        mp.nq_lists = (int)nq;
+        mp.out_scores = out_scores;
+        mp.out_ids = reinterpret_cast<long long*>(out_ids);
+        if ((rc = launch_merge(idx, mp, (int)nq, 0, s)) != B2S_OK) return rc;
+        idx->stats.kernel_launches++;
+        if (idx->opt_timing) {
+            cudaEventRecord(idx->ev[1], s);
+            cudaEventRecord(idx->ev[2], s);
+            cudaEventRecord(idx->ev[3], s);
+        }
+        return B2S_OK;
+    }
     if (idx->n == 0) {
         const long long cnt = (long long)nq * k;
         fill_empty_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(out_scores, reinterpret_cast<long long*>(out_ids), cnt);
@@ -395,9 +439,21 @@ int ensure_pinned(void** p, size_t* have, size_t need) {
 // extern "C"
 // =============================================================================================
 
+static void exchange_release(b2s_index* idx) {
+    auto& ex = idx->ex;
+    for (void* m : ex.opened) cudaIpcCloseMemHandle(m);
+    ex.opened.clear();
+    if (ex.peers_dev) cudaFree(ex.peers_dev);
+    if (ex.status) cudaFree(ex.status);
+    if (ex.local) cudaFree(ex.local);
+    ex = b2s_index::Exchange();
+    cudaGetLastError();
+}
+
+
 extern "C" {
 
-B2S_API int b2s_version(void) { return 100; }
+B2S_API int b2s_version(void) { return 101; }
 
 B2S_API const char* b2s_last_error(void) { return g_err.c_str(); }
 
@@ -465,6 +521,7 @@ B2S_API int b2s_destroy(b2s_index* idx) {
 #ifndef B2S_NO_TENSOR_PATH
     tensor_path_release(idx);
 #endif
+    exchange_release(idx);
     if (idx->pin_q) cudaFreeHost(idx->pin_q);
     if (idx->pin_out) cudaFreeHost(idx->pin_out);
     if (idx->ring) {
@@ -856,6 +913,163 @@ B2S_API int b2s_ance_filter_device(int device, const float* cand_scores, const i
         cand_scores, reinterpret_cast<const long long*>(cand_ids), k_in, reinterpret_cast<const long long*>(pos_ids),
         pos_scores, n_pos, margin, top_k, nq, reinterpret_cast<long long*>(out_ids), out_scores, out_counts);
     CUDA_TRY(cudaGetLastError());
+    return B2S_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cross-GPU exchange (exchange.cuh)
+// ---------------------------------------------------------------------------------------------
+B2S_API int b2s_exchange_create(b2s_index* idx, int world, int rank, int64_t slot_bytes, int max_nq,
+                                void* ipc_handle_out) {
+    if (!idx || world < 1 || rank < 0 || rank >= world || slot_bytes < 16 || max_nq < 1)
+        return fail(B2S_ERR_INVALID, "bad arguments");
+    if (world > 64) return fail(B2S_ERR_UNSUPPORTED, "at most 64 ranks");
+    std::lock_guard<std::mutex> g(idx->mu);
+    int rc = use_device(idx);
+    if (rc != B2S_OK) return rc;
+    exchange_release(idx);
+    auto& ex = idx->ex;
+    ex.world = world;
+    ex.rank = rank;
+    ex.max_nq = max_nq;
+    ex.slot_stride = (slot_bytes + 255) / 256 * 256;
+    ex.flags_off = 2ll * world * ex.slot_stride;
+    ex.bytes = (size_t)ex.flags_off + (size_t)2 * world * max_nq * sizeof(unsigned);
+    CUDA_TRY(cudaMalloc((void**)&ex.local, ex.bytes));
+    CUDA_TRY(cudaMemset(ex.local, 0, ex.bytes));
+    CUDA_TRY(cudaMalloc((void**)&ex.status, sizeof(unsigned)));
+    CUDA_TRY(cudaMemset(ex.status, 0, sizeof(unsigned)));
+    CUDA_TRY(cudaMalloc((void**)&ex.peers_dev, sizeof(unsigned char*) * world));
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t h;
+        CUDA_TRY(cudaIpcGetMemHandle(&h, ex.local));
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        memcpy(ipc_handle_out, &h, 64);
+    }
+    return B2S_OK;
+}
+
+B2S_API void* b2s_exchange_local(const b2s_index* idx) { return idx ? idx->ex.local : nullptr; }
+
+B2S_API int b2s_exchange_connect(b2s_index* idx, const void* handles, int raw_pointers) {
+    if (!idx || !handles) return fail(B2S_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> g(idx->mu);
+    auto& ex = idx->ex;
+    if (!ex.local) return fail(B2S_ERR_INVALID, "b2s_exchange_create was not called");
+    int rc = use_device(idx);
+    if (rc != B2S_OK) return rc;
+    std::vector<unsigned char*> peers(ex.world, nullptr);
+    for (int r = 0; r < ex.world; ++r) {
+        if (r == ex.rank) {
+            peers[r] = ex.local;
+        } else if (raw_pointers) {
+            peers[r] = reinterpret_cast<unsigned char* const*>(handles)[r];   // same-process ranks (tests)
+        } else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, reinterpret_cast<const unsigned char*>(handles) + (size_t)r * 64, 64);
+            void* m = nullptr;
+            CUDA_TRY(cudaIpcOpenMemHandle(&m, h, cudaIpcMemLazyEnablePeerAccess));
+            ex.opened.push_back(m);
+            peers[r] = reinterpret_cast<unsigned char*>(m);
+        }
+        if (!peers[r]) return fail(B2S_ERR_INVALID, "null peer buffer");
+    }
+    CUDA_TRY(cudaMemcpy(ex.peers_dev, peers.data(), sizeof(unsigned char*) * ex.world, cudaMemcpyHostToDevice));
+    ex.connected = true;
+    return B2S_OK;
+}
+
+B2S_API int b2s_exchange_status(b2s_index* idx) {
+    if (!idx || !idx->ex.status) return 0;
+    unsigned v = 0;
+    cudaSetDevice(idx->device);
+    if (cudaMemcpy(&v, idx->ex.status, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return (int)v;
+}
+
+static int search_sharded_impl(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, int k,
+                               float* out_scores, int64_t* out_ids, void* cuda_stream, int phase) {
+    auto& ex = idx->ex;
+    if (!ex.connected) return fail(B2S_ERR_INVALID, "exchange is not connected");
+    if (nq > ex.max_nq || b2s_packed_bytes(nq, k) > ex.slot_stride || (int64_t)ex.world * k > kMergeSortCap)
+        return fail(B2S_ERR_UNSUPPORTED, "sharded search: (nq, k) exceeds the exchange buffer; use the all-gather path");
+    int rc = use_device(idx);
+    if (rc != B2S_OK) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    ExchangeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.peer_base = ex.peers_dev;
+    a.local_base = ex.local;
+    a.world = ex.world;
+    a.rank = ex.rank;
+    a.slot_stride = ex.slot_stride;
+    a.flags_off = ex.flags_off;
+    a.max_nq = ex.max_nq;
+    a.nq = nq;
+    a.timeout_cycles = 4000000000ll;   // ~2 s: a missing peer must not hang the GPU
+    a.status = ex.status;
+    a.out_scores = out_scores;
+    a.out_ids = reinterpret_cast<long long*>(out_ids);
+    if (phase != 2) {
+        a.seq = ++ex.seq;
+        // one kernel when every CTA of the merge is co-resident on every rank, else push / wait split
+        idx->ex_fused = (phase == 0 && nq <= idx->num_sms) ? 1 : 0;
+        idx->ex_call = &a;
+        rc = search_impl(idx, queries, q_dtype, nq, k, out_scores, out_ids, s);
+        idx->ex_call = nullptr;
+        if (rc != B2S_OK) return rc;
+        if (idx->ex_fused || phase == 1) return B2S_OK;
+    } else {
+        a.seq = ex.seq;
+    }
+    exchange_wait_merge_kernel<<<(unsigned)nq, kMergeThreads, 0, s>>>(a, k);
+    CUDA_TRY(cudaGetLastError());
+    idx->stats.kernel_launches++;
+    return B2S_OK;
+}
+
+B2S_API int b2s_search_sharded_device(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, int k,
+                                      float* out_scores, int64_t* out_ids, void* cuda_stream, int phase) {
+    if (!idx) return fail(B2S_ERR_INVALID, "null index");
+    if (nq < 0 || k < 0) return fail(B2S_ERR_INVALID, "nq and k must be >= 0");
+    if (nq == 0 || k == 0) return B2S_OK;
+    if (phase < 0 || phase > 2) return fail(B2S_ERR_INVALID, "phase must be 0 (whole call), 1 (push) or 2 (wait+merge)");
+    std::lock_guard<std::mutex> g(idx->mu);
+    return search_sharded_impl(idx, queries, q_dtype, nq, k, out_scores, out_ids, cuda_stream, phase);
+}
+
+B2S_API int b2s_search_sharded(b2s_index* idx, const float* queries, int64_t nq, int k, float* out_scores,
+                               int64_t* out_ids) {
+    if (!idx) return fail(B2S_ERR_INVALID, "null index");
+    if (nq < 0 || k < 0) return fail(B2S_ERR_INVALID, "nq and k must be >= 0");
+    if (nq == 0 || k == 0) return B2S_OK;
+    if (!queries || !out_scores || !out_ids) return fail(B2S_ERR_INVALID, "null buffer");
+    std::lock_guard<std::mutex> g(idx->mu);
+    int rc = use_device(idx);
+    if (rc != B2S_OK) return rc;
+    const size_t qbytes = (size_t)nq * idx->dim * sizeof(float);
+    const size_t sbytes = (size_t)nq * k * sizeof(float);
+    const size_t ibytes = (size_t)nq * k * sizeof(int64_t);
+    if ((rc = idx->ws_io_q.ensure(qbytes)) != B2S_OK) return rc;
+    if ((rc = idx->ws_io_scores.ensure(sbytes)) != B2S_OK) return rc;
+    if ((rc = idx->ws_io_ids.ensure(ibytes)) != B2S_OK) return rc;
+    if ((rc = ensure_pinned(&idx->pin_q, &idx->pin_q_bytes, qbytes)) != B2S_OK) return rc;
+    if ((rc = ensure_pinned(&idx->pin_out, &idx->pin_out_bytes, sbytes + ibytes)) != B2S_OK) return rc;
+    memcpy(idx->pin_q, queries, qbytes);
+    CUDA_TRY(cudaMemcpyAsync(idx->ws_io_q.p, idx->pin_q, qbytes, cudaMemcpyHostToDevice, idx->stream));
+    rc = search_sharded_impl(idx, idx->ws_io_q.p, B2S_DTYPE_F32, nq, k, reinterpret_cast<float*>(idx->ws_io_scores.p),
+                             reinterpret_cast<int64_t*>(idx->ws_io_ids.p), idx->stream, 0);
+    if (rc != B2S_OK) return rc;
+    unsigned char* po = reinterpret_cast<unsigned char*>(idx->pin_out);
+    CUDA_TRY(cudaMemcpyAsync(po, idx->ws_io_ids.p, ibytes, cudaMemcpyDeviceToHost, idx->stream));
+    CUDA_TRY(cudaMemcpyAsync(po + ibytes, idx->ws_io_scores.p, sbytes, cudaMemcpyDeviceToHost, idx->stream));
+    CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    memcpy(out_ids, po, ibytes);
+    memcpy(out_scores, po + ibytes, sbytes);
     return B2S_OK;
 }
 

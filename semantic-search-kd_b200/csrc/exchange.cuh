@@ -1,0 +1,147 @@
+// exchange.cuh -- cross-GPU candidate exchange fused with the per-query merge (row-sharded corpus).
+//
+// The reference has no multi-device search; its scaling prose ("shard across instances, fan out,
+// merge": /root/reference/docs/operations/scaling-and-performance.md:154-172) becomes: every rank
+// finds the local top-k of its shard, the ranks exchange k candidates per query, every rank merges
+// G*k candidates.  Instead of local-merge kernel -> NCCL all-gather -> merge kernel, ONE kernel does
+// all three: the CTA that has merged query q's local candidates stores them straight into every
+// peer's exchange buffer over NVLink (peer-mapped memory, plain st.global + a release flag per
+// (source rank, query)), waits for the peers' flags for q in its OWN memory, and merges.
+//
+// Exchange buffer of one rank (cudaMalloc'd, exported with cudaIpcGetMemHandle, mapped by peers):
+//   slots [2 parities][world source ranks][slot_stride bytes] : packed block of the source rank
+//          ([ids int64 nq*k][scores f32 nq*k]), written by that rank
+//   flags [2 parities][world][max_nq] u32                      : sequence number of the call
+// Parity = seq & 1.  A rank can only start call seq+2 after it has seen every peer's flags of call
+// seq+1, which a peer publishes after it finished reading the slots of call seq, so two slot sets
+// suffice.  All ranks must issue the same sequence of sharded calls (same nq, k).
+//
+// FUSED = true needs all nq CTAs of every rank co-resident (a CTA pushes before it waits, but a
+// not-yet-scheduled CTA cannot push): the host uses it for nq <= #SMs and otherwise launches the
+// push (FUSED = false) and the wait+merge (exchange_wait_merge_kernel) as two kernels, which is
+// deadlock-free for any nq because push kernels never wait.
+#pragma once
+#include "merge_topk.cuh"
+
+namespace b2s {
+
+struct ExchangeArgs {
+    unsigned char* const* peer_base;   // device array [world]: exchange buffer base of every rank as mapped here
+    unsigned char* local_base;         // == peer_base[rank]
+    int world;
+    int rank;
+    long long slot_stride;             // bytes per (parity, source rank) slot
+    long long flags_off;               // byte offset of the flag region
+    int max_nq;                        // flags per (parity, source rank)
+    unsigned seq;                      // sequence number of this call (>= 1)
+    long long nq;                      // queries of the whole call
+    int q_offset;                      // global index of this launch's query 0
+    long long timeout_cycles;          // spin budget; on expiry *status = seq and the result is garbage
+    unsigned* status;                  // device word, 0 = ok
+    float* out_scores;                 // [nq, k] final
+    long long* out_ids;
+};
+
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Store this rank's sorted top-k of global query gq (keys in buf[0..kk)) into every rank's slot and
+// publish the flag.  Block-wide.
+__device__ __forceinline__ void exchange_push(const ExchangeArgs& ex, const MergeParams& p, const u64* buf, int kk,
+                                              long long gq) {
+    const int tid = threadIdx.x;
+    const int parity = (int)(ex.seq & 1u);
+    const long long slot = ((long long)parity * ex.world + ex.rank) * ex.slot_stride;
+    const long long ids_off = slot + (gq * p.k) * 8;
+    const long long sc_off = slot + ex.nq * p.k * 8 + (gq * p.k) * 4;
+    for (int e = tid; e < p.k * ex.world; e += kMergeThreads) {
+        const int peer = e / p.k, i = e - peer * p.k;
+        float s = -FLT_MAX;
+        long long id = -1;
+        if (i < kk) {
+            const u64 key = buf[i];
+            s = key_score(key);
+            id = (long long)key_row(key) + p.id_offset;
+        }
+        unsigned char* base = ex.peer_base[peer];
+        *reinterpret_cast<long long*>(base + ids_off + (long long)i * 8) = id;
+        *reinterpret_cast<float*>(base + sc_off + (long long)i * 4) = s;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < ex.world) {
+        unsigned* flag = reinterpret_cast<unsigned*>(ex.peer_base[tid] + ex.flags_off) +
+                         ((long long)parity * ex.world + ex.rank) * ex.max_nq + gq;
+        st_release_sys_u32(flag, ex.seq);
+    }
+}
+
+// Wait for every rank's candidates of global query gq, merge world*k of them, write the final top-k.
+__device__ __forceinline__ void exchange_wait_merge(const ExchangeArgs& ex, int k, u64* buf, long long gq) {
+    const int tid = threadIdx.x;
+    const int parity = (int)(ex.seq & 1u);
+    if (tid < ex.world) {
+        const unsigned* flag = reinterpret_cast<const unsigned*>(ex.local_base + ex.flags_off) +
+                               ((long long)parity * ex.world + tid) * ex.max_nq + gq;
+        const long long t0 = clock64();
+        while (ld_acquire_sys_u32(flag) != ex.seq) {
+            if (clock64() - t0 > ex.timeout_cycles) {
+                atomicExch(ex.status, ex.seq);
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    const int total = ex.world * k;   // host guarantees total <= kMergeSortCap
+    for (int e = tid; e < total; e += kMergeThreads) {
+        const int r = e / k, i = e - r * k;
+        const unsigned char* slot = ex.local_base + ((long long)parity * ex.world + r) * ex.slot_stride;
+        const long long id = __ldcg(reinterpret_cast<const long long*>(slot + (gq * k + i) * 8));
+        const float s = __ldcg(reinterpret_cast<const float*>(slot + ex.nq * k * 8 + (gq * k + i) * 4));
+        // position e = rank-major, then local order: keeps (score desc, id asc) across shards
+        buf[e] = id < 0 ? 0ull : make_key(s, (uint32_t)e);
+    }
+    __syncthreads();
+    block_sort_desc(buf, total > 0 ? total : 1, tid);
+    for (int i = tid; i < k; i += kMergeThreads) {
+        float s = -FLT_MAX;
+        long long id = -1;
+        if (i < total && buf[i] != 0ull) {
+            const int pos = (int)key_row(buf[i]);
+            const int r = pos / k, j = pos - r * k;
+            const unsigned char* slot = ex.local_base + ((long long)parity * ex.world + r) * ex.slot_stride;
+            id = __ldcg(reinterpret_cast<const long long*>(slot + (gq * k + j) * 8));
+            s = __ldcg(reinterpret_cast<const float*>(slot + ex.nq * k * 8 + (gq * k + j) * 4));
+        }
+        ex.out_scores[gq * k + i] = s;
+        ex.out_ids[gq * k + i] = id;
+    }
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(kMergeThreads) merge_exchange_kernel(const MergeParams p, const ExchangeArgs ex) {
+    __shared__ MergeSmem sm;
+    const int q = blockIdx.x;
+    const long long gq = (long long)ex.q_offset + q;
+    const int m_sorted = merge_lists_sorted(p, q, sm);
+    const int kk = m_sorted < p.k ? m_sorted : p.k;
+    exchange_push(ex, p, sm.buf, kk, gq);
+    if (FUSED) {
+        __syncthreads();
+        exchange_wait_merge(ex, p.k, sm.buf, gq);
+    }
+}
+
+__global__ void __launch_bounds__(kMergeThreads) exchange_wait_merge_kernel(const ExchangeArgs ex, int k) {
+    __shared__ u64 buf[kMergeSortCap];
+    exchange_wait_merge(ex, k, buf, (long long)ex.q_offset + blockIdx.x);
+}
+
+}  // namespace b2s

@@ -185,7 +185,7 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
         mp.id_offset = idx->id_offset;
         mp.out_scores = out_scores + (size_t)c0 * k;
         mp.out_ids = reinterpret_cast<long long*>(out_ids) + (size_t)c0 * k;
-        if ((rc = launch_merge(mp, cn, s)) != B2S_OK) return rc;
+        if ((rc = launch_merge(idx, mp, cn, (int)c0, s)) != B2S_OK) return rc;
         idx->stats.kernel_launches++;
     }
     return B2S_OK;

@@ -74,20 +74,35 @@ __device__ __forceinline__ u64 fetch_candidate(const MergeParams& p, const int* 
     return p.lists[((size_t)lo * p.nq_lists + q) * p.cap + (e - offs[lo])];
 }
 
-__global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergeParams p) {
-    __shared__ u64 buf[kMergeSortCap];
-    __shared__ int offs[kMergeMaxLists + 1];
-    __shared__ __align__(16) int hist[kRadixBins];
-    __shared__ int s_fill;
-    __shared__ u64 s_prefix;      // selected high bits so far
-    __shared__ int s_bits_done;   // number of high bits fixed in s_prefix
-    __shared__ int s_k_rem;       // rank still to find inside the current bucket
-    __shared__ int s_bucket_cnt;  // candidates inside the current bucket
-    __shared__ u64 sel[kMergeFastCap];
-    __shared__ u64 s_floor;
-    __shared__ int s_nonempty;
+struct MergeSmem {
+    u64 buf[kMergeSortCap];
+    int offs[kMergeMaxLists + 1];
+    __align__(16) int hist[kRadixBins];
+    int s_fill;
+    u64 s_prefix;      // selected high bits so far
+    int s_bits_done;   // number of high bits fixed in s_prefix
+    int s_k_rem;       // rank still to find inside the current bucket
+    int s_bucket_cnt;  // candidates inside the current bucket
+    u64 sel[kMergeFastCap];
+    u64 s_floor;
+    int s_nonempty;
+};
 
-    const int q = blockIdx.x;
+// Block-wide: leave the best min(m, k..) candidate keys of query q sorted descending in sm.buf and
+// return how many of them are valid (>= min(k, total candidates)).
+__device__ __forceinline__ int merge_lists_sorted(const MergeParams& p, const int q, MergeSmem& sm) {
+    u64* buf = sm.buf;
+    int* offs = sm.offs;
+    int* hist = sm.hist;
+    int& s_fill = sm.s_fill;
+    u64& s_prefix = sm.s_prefix;
+    int& s_bits_done = sm.s_bits_done;
+    int& s_k_rem = sm.s_k_rem;
+    int& s_bucket_cnt = sm.s_bucket_cnt;
+    u64* sel = sm.sel;
+    u64& s_floor = sm.s_floor;
+    int& s_nonempty = sm.s_nonempty;
+
     const int tid = threadIdx.x;
     const int L = p.num_lists;    // host guarantees L <= kMergeMaxLists
 
@@ -231,6 +246,15 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergePa
     }
 
     if (!sorted_done) block_sort_desc(buf, m_sorted > 0 ? m_sorted : 1, tid);
+    return m_sorted;
+}
+
+__global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergeParams p) {
+    __shared__ MergeSmem sm;
+    const int q = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int m_sorted = merge_lists_sorted(p, q, sm);
+    const u64* buf = sm.buf;
 
     const int kk = m_sorted < p.k ? m_sorted : p.k;
     for (int i = tid; i < p.k; i += kMergeThreads) {

@@ -5,7 +5,12 @@ range ``[r*ceil(N/G), min(N, (r+1)*ceil(N/G)))``; global id = range start + loca
 ``doc_ids[idx]`` mapping of ``/root/reference/src/serve/app.py:303`` is unchanged.  Queries are
 replicated (``dim*4`` bytes each).  A search is
 
-    local top-k on every rank (K1/K2 + K3, ids already global)
+    exchange="peer" (default with NCCL/CUDA): K1/K2, then ONE fused kernel per query batch that merges
+      the local lists, stores the local top-k (k*12 bytes per query) straight into every peer's
+      exchange buffer over NVLink (CUDA-IPC mapped memory + release flags), waits for the peers'
+      flags and merges G*k candidates (csrc/exchange.cuh; ``b2s_search_sharded_device``).  No
+      collective call on the data path; torch.distributed only carries the 64-byte IPC handles once.
+    exchange="nccl": local top-k on every rank (K1/K2 + K3, ids already global)
       -> ONE all-gather of the packed candidate block (k*12 bytes per query per rank) over NVLink
       -> K4 merge of G*k candidates per query on every rank (ties -> lower id).
 
@@ -53,7 +58,8 @@ class ShardedFlatIPIndex:
 
     def __init__(self, embedding_dim: int = 384, metric: str = "cosine", group=None,
                  local_index: Optional[FlatIPIndex] = None,
-                 merge_fn: Optional[Callable] = None, device: Optional[int] = None) -> None:
+                 merge_fn: Optional[Callable] = None, device: Optional[int] = None,
+                 exchange: str = "auto", exchange_slot_bytes: int = 4 << 20, exchange_max_nq: int = 16384) -> None:
         if dist is None or not dist.is_initialized():
             raise IndexBuildError("torch.distributed must be initialised before ShardedFlatIPIndex")
         self.group = group
@@ -63,6 +69,18 @@ class ShardedFlatIPIndex:
         self.local = local_index if local_index is not None else FlatIPIndex(embedding_dim, metric=metric,
                                                                               device=device)
         self._merge_fn = merge_fn
+        if exchange not in ("auto", "peer", "nccl"):
+            raise IndexBuildError("exchange must be 'auto', 'peer' or 'nccl'")
+        # the fused peer-memory exchange needs real GPUs and the CUDA merge (not the injected test doubles)
+        if exchange == "auto":
+            exchange = "peer" if (merge_fn is None and local_index is None or
+                                  (merge_fn is None and isinstance(local_index, FlatIPIndex))) and \
+                                 torch is not None and torch.cuda.is_available() and \
+                                 dist.get_backend(group) == "nccl" else "nccl"
+        self.exchange = exchange
+        self._ex_slot_bytes = int(exchange_slot_bytes)
+        self._ex_max_nq = int(exchange_max_nq)
+        self._ex_ready = False
         self.n_total = 0
         self.range = (0, 0)
         self._bufs = {}
@@ -107,11 +125,51 @@ class ShardedFlatIPIndex:
             self._bufs = {key: b}  # keep only the latest shape
         return b
 
+    def _connect_exchange(self, device) -> None:
+        """One-time set-up of the peer-memory exchange: allocate this rank's buffer, all-gather the
+        64-byte CUDA IPC handles, map every peer's buffer."""
+        L = _lib.lib()
+        h = self.local._ensure()
+        handle = (ctypes.c_ubyte * 64)()
+        _check(L.b2s_exchange_create(h, self.world, self.rank, self._ex_slot_bytes, self._ex_max_nq, handle),
+               "b2s_exchange_create")
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+        allh = torch.empty((self.world * 64,), dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        buf = np.ascontiguousarray(allh.cpu().numpy())
+        _check(L.b2s_exchange_connect(h, buf.ctypes.data_as(ctypes.c_void_p), 0), "b2s_exchange_connect")
+        dist.barrier(group=self.group)   # every rank has mapped every buffer before anyone pushes
+        self._ex_ready = True
+
+    def _peer_ok(self, nq: int, k: int) -> bool:
+        return (self.exchange == "peer" and self.world > 1 and nq <= self._ex_max_nq and
+                packed_bytes(nq, k) <= self._ex_slot_bytes and self.world * k <= 4096)
+
     def search_device(self, q: "torch.Tensor", k: int):
         """Device-resident sharded search on the current stream; returns CUDA tensors (all ranks)."""
         if self.n_total == 0 and self.local.ntotal == 0 and self.local._h is None:
             raise IndexNotBuiltError()
         nq = q.shape[0]
+        if nq and k and self._peer_ok(nq, k):
+            if not self._ex_ready:
+                self._connect_exchange(q.device)
+            if q.dtype not in (torch.float32, torch.bfloat16):
+                q = q.float()
+            q = q.contiguous()
+            key = ("peer", nq, k, str(q.device))
+            b = self._bufs.get(key)
+            if b is None:
+                b = (torch.empty((nq, k), dtype=torch.float32, device=q.device),
+                     torch.empty((nq, k), dtype=torch.int64, device=q.device))
+                self._bufs = {key: b}
+            out_s, out_i = b
+            stream = torch.cuda.current_stream(q.device).cuda_stream
+            dt = _lib.DTYPE_BF16 if q.dtype == torch.bfloat16 else _lib.DTYPE_F32
+            _check(_lib.lib().b2s_search_sharded_device(self.local._h, ctypes.c_void_p(q.data_ptr()), dt, nq, int(k),
+                                                        ctypes.c_void_p(out_s.data_ptr()),
+                                                        ctypes.c_void_p(out_i.data_ptr()), ctypes.c_void_p(stream), 0),
+                   "b2s_search_sharded_device")
+            return out_s, out_i
         gathered, mine, scores, ids, out_s, out_i = self._buffers(nq, k, q.device)
         self.local.search_device(q, k, out=(scores, ids))
         if self.world > 1:
@@ -135,6 +193,16 @@ class ShardedFlatIPIndex:
         if q.ndim == 1:
             q = q.reshape(1, -1)
         dev = torch.device("cuda", self.local.device if self.local.device is not None else torch.cuda.current_device())
+        nq = q.shape[0]
+        if nq and k and self._peer_ok(nq, k):
+            if not self._ex_ready:
+                self._connect_exchange(dev)
+            scores = np.empty((nq, k), dtype=np.float32)
+            ids = np.empty((nq, k), dtype=np.int64)
+            _check(_lib.lib().b2s_search_sharded(self.local._h, q.ctypes.data_as(ctypes.c_void_p), nq, int(k),
+                                                 scores.ctypes.data_as(ctypes.c_void_p),
+                                                 ids.ctypes.data_as(ctypes.c_void_p)), "b2s_search_sharded")
+            return scores, ids
         qd = torch.from_numpy(q).to(dev, non_blocking=False)
         s, i = self.search_device(qd, k)
         return s.cpu().numpy(), i.cpu().numpy()
