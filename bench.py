@@ -306,6 +306,22 @@ def run_ours(args):
     dom = dom[:got][dom[:got] > 0]
     k1_ms = float(dom.mean()) if len(dom) else float("nan")
 
+    # ---- informational: back-to-back device calls with the scan of query i+1 overlapping the merge
+    # (and, multi-GPU, the exchange) of query i -- option "pdl"=2; the query buffer is static here
+    local.set_option("timing", 0)
+    local.set_option("pdl", 2)
+    for i in range(5):
+        step_dev(i)
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for i in range(args.steps):
+        step_dev(args.warmup + i)
+    p1.record()
+    barrier()
+    pipe_ms = p0.elapsed_time(p1)
+    local.set_option("pdl", 1)
+
     # ---- e2e: host buffers through the public search(), copies inside the timed region -------
     e2e_steps = max(10, min(args.steps, args.e2e_steps))
     for i in range(3):
@@ -323,9 +339,9 @@ def run_ours(args):
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([ms, e2e_s, k1_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, k1_ms, pipe_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s, k1_ms = [float(x) for x in t.tolist()]
+        ms, e2e_s, k1_ms, pipe_ms = [float(x) for x in t.tolist()]
 
     # sanity: device path and host path agree on a query
     sd, idd = idx.search_device(Qd[5:6], K)
@@ -362,6 +378,10 @@ def run_ours(args):
                                "device_p99": float(np.percentile(tot, 99)) if len(tot) else None,
                                "note": "e2e = wall time of one search(np.ndarray, k) call on rank 0; device = CUDA events "
                                        "around one whole search call inside the timed region (rank 0)"},
+                "pipelined": {"value": args.steps / (pipe_ms * 1e-3), "unit": "queries/s", "ms_per_step": pipe_ms / args.steps,
+                              "note": "NOT the headline: same K steps with option pdl=2 (programmatic dependent launch lets "
+                                      "the scan of query i+1 overlap the merge/exchange of query i; needs a query buffer "
+                                      "that is not written by the immediately preceding kernel)"},
                 "gpu_launches": launches_per_step * args.steps,
                 "clocks": clk, "build_s": round(t_build, 2), "paths_agree": agree}
         if n_gpus == 1 and not args.no_batched:

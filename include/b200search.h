@@ -99,6 +99,13 @@ B2S_API int b2s_set_id_offset(b2s_index* idx, int64_t offset);
  *   "keep_f32"    1: keep an fp32 copy of added rows for exact re-scoring
  *   "rescore_pad" extra candidates re-scored in fp32 when keep_f32 is on
  *   "timing"      1: record CUDA-event timings into b2s_stats (adds syncs)
+ *   "pdl"         0 off | 1 (default) programmatic dependent launch hides the launch latency
+ *                 between the scan and merge kernels | 2 additionally lets the scan of call i+1
+ *                 overlap the merge of call i; valid only if the query buffer of a call is not
+ *                 written by the kernel enqueued immediately before it on the same stream
+ *   "tc_min_nq"   smallest query batch that takes the tensor path (default 3)
+ *   "tc_sample_div"  threshold pre-pass samples 1/div of the corpus tiles (0 = chosen by k)
+ *   "tc_chunk_tiles" tiles per work item when several query blocks share the corpus
  */
 B2S_API int b2s_set_option(b2s_index* idx, const char* name, int64_t value);
 B2S_API int64_t b2s_get_option(const b2s_index* idx, const char* name);

@@ -104,6 +104,10 @@ struct b2s_index {
     int opt_rescore_pad = 32;
     int opt_timing = 0;
     int opt_tc_min_nq = 3;
+    int opt_pdl = 1;              // 1: programmatic dependent launch hides launch latencies (always safe);
+                                  // 2: also overlap the scan of call i+1 with the merge of call i -- only
+                                  //    valid when the query buffer is not written by the kernel enqueued
+                                  //    immediately before the search on the same stream
     int opt_tc_sample_div = 0;    // the threshold pre-pass samples 1 / this of the full tiles (0 = by k)
     int opt_tc_chunk_lo = 48;     // tiles per work item when several query blocks share the corpus
     int opt_tc_chunk_hi = 96;
@@ -188,13 +192,32 @@ int grow_rows(b2s_index* idx, int64_t need_rows) {
 // K1 dispatch
 // ---------------------------------------------------------------------------------------------
 
+bool g_pdl_enabled = true;   // process-wide switch ("pdl" option 0 turns it off for debugging)
+
+// Launch with programmatic dependent launch allowed: the kernel may begin while its predecessor in
+// the stream is still running and synchronises on it with grid_dep_wait() (select.cuh).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = g_pdl_enabled ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <int CPL, int NQ, int U>
 int launch_scan_t(const ScanParams& p, int grid, cudaStream_t s) {
     const size_t smem = (size_t)NQ * p.cap * sizeof(u64);
     auto kern = scan_topk_kernel<CPL, NQ, U>;
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kScanThreads, smem, s>>>(p);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(kScanThreads), smem, s, p));
     return B2S_OK;
 }
 
@@ -234,18 +257,17 @@ int launch_merge(const b2s_index* idx, const MergeParams& mp, int nq, int q_offs
     if (idx->ex_call != nullptr && mp.out_kth_key == nullptr) {
         ExchangeArgs ex = *idx->ex_call;
         ex.q_offset = q_offset;
-        if (idx->ex_fused) merge_exchange_kernel<true><<<nq, kMergeThreads, 0, s>>>(mp, ex);
-        else merge_exchange_kernel<false><<<nq, kMergeThreads, 0, s>>>(mp, ex);
+        if (idx->ex_fused) CUDA_TRY(launch_pdl(merge_exchange_kernel<true>, dim3(nq), dim3(kMergeThreads), 0, s, mp, ex));
+        else CUDA_TRY(launch_pdl(merge_exchange_kernel<false>, dim3(nq), dim3(kMergeThreads), 0, s, mp, ex));
     } else {
-        merge_topk_kernel<<<nq, kMergeThreads, 0, s>>>(mp);
+        CUDA_TRY(launch_pdl(merge_topk_kernel, dim3(nq), dim3(kMergeThreads), 0, s, mp));
     }
-    CUDA_TRY(cudaGetLastError());
     return B2S_OK;
 }
 
 // Scan path for queries [0, nq) already in fp32 on the device.
 int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* out_scores,
-                int64_t* out_ids, cudaStream_t s, bool seed) {
+                int64_t* out_ids, cudaStream_t s, bool seed, bool late_wait_ok) {
     const int cap = list_capacity(k);
     const int rpi = scan_rows_per_iter(idx->dim);
     const int unit = rpi * kScanWarps;
@@ -282,6 +304,9 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
                 p.lists = reinterpret_cast<u64*>(idx->ws_lists.p);
                 p.counts = reinterpret_cast<int*>(idx->ws_counts.p);
                 p.nq_lists = chunk;
+                // The scan only READS the corpus and the caller's queries unless a kernel of THIS call
+                // ran before it (query prep, seeding pass, an earlier group writing the same workspace).
+                p.pdl_late_wait = (late_wait_ok && !seed && nq <= max_group) ? 1 : 0;
                 if ((rc = launch_scan(idx->dim, group, p, grid, s)) != B2S_OK) return rc;
                 idx->stats.kernel_launches++;
                 if (pass == 1) idx->stats.passes++;
@@ -401,7 +426,10 @@ int search_impl(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, in
             qf = reinterpret_cast<const float*>(idx->ws_qf32.p);
         }
         if (idx->opt_timing) cudaEventRecord(idx->ev[1], s);
-        rc = search_scan(idx, qf, nq, k, out_scores, out_ids, s, seed);
+        // late PDL wait only if no kernel of this call precedes the scan and no event sits between
+        // consecutive calls' kernels (timing on) -- see scan_topk.cuh
+        const bool late_wait_ok = (qf == reinterpret_cast<const float*>(queries)) && idx->opt_pdl == 2;
+        rc = search_scan(idx, qf, nq, k, out_scores, out_ids, s, seed, late_wait_ok);
         if (rc != B2S_OK) return rc;
     } else {
 #ifndef B2S_NO_TENSOR_PATH
@@ -658,6 +686,10 @@ B2S_API int b2s_set_option(b2s_index* idx, const char* name, int64_t value) {
         idx->ev_valid = false;
     } else if (s == "tc_min_nq") {
         idx->opt_tc_min_nq = (int)std::max<int64_t>(1, value);
+    } else if (s == "pdl") {
+        if (value < 0 || value > 2) return fail(B2S_ERR_INVALID, "pdl must be 0, 1 or 2");
+        idx->opt_pdl = (int)value;
+        g_pdl_enabled = value != 0;
     } else if (s == "tc_sample_div") {
         idx->opt_tc_sample_div = (int)std::min<int64_t>(1 << 20, std::max<int64_t>(0, value));
     } else if (s == "tc_chunk_tiles") {
@@ -679,6 +711,7 @@ B2S_API int64_t b2s_get_option(const b2s_index* idx, const char* name) {
     if (s == "rescore_pad") return idx->opt_rescore_pad;
     if (s == "timing") return idx->opt_timing;
     if (s == "tc_min_nq") return idx->opt_tc_min_nq;
+    if (s == "pdl") return idx->opt_pdl;
     if (s == "tc_sample_div") return idx->opt_tc_sample_div;
     if (s == "tc_chunk_tiles") return idx->opt_tc_chunk_lo == idx->opt_tc_chunk_hi ? idx->opt_tc_chunk_lo : 0;
     if (s == "num_sms") return idx->num_sms;

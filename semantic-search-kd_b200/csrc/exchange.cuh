@@ -130,6 +130,8 @@ __global__ void __launch_bounds__(kMergeThreads) merge_exchange_kernel(const Mer
     __shared__ MergeSmem sm;
     const int q = blockIdx.x;
     const long long gq = (long long)ex.q_offset + q;
+    grid_dep_launch();
+    grid_dep_wait();
     const int m_sorted = merge_lists_sorted(p, q, sm);
     const int kk = m_sorted < p.k ? m_sorted : p.k;
     exchange_push(ex, p, sm.buf, kk, gq);

@@ -253,6 +253,8 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergePa
     __shared__ MergeSmem sm;
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
+    grid_dep_launch();   // PDL: the next kernel of the stream may start; it waits for us where it must
+    grid_dep_wait();     // the producer of the candidate lists has completed
     const int m_sorted = merge_lists_sorted(p, q, sm);
     const u64* buf = sm.buf;
 

@@ -36,6 +36,9 @@ struct ScanParams {
     u64* lists;            // out [gridDim.x, nq_lists, cap]
     int* counts;           // out [gridDim.x, nq_lists]
     int nq_lists;          // stride (in queries) of the list arrays
+    int pdl_late_wait;     // 1: nothing this kernel READS is produced by the preceding kernel of the
+                           // stream, so the PDL wait is deferred to just before the list write-out
+                           // (the scan of query i+1 then overlaps the merge of query i)
 };
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
@@ -78,6 +81,7 @@ scan_topk_kernel(const ScanParams p) {
     constexpr int kChunksPerRow = CPL * 16;  // uint4 per row
     constexpr int kRowsPerIter = 2 * U;
 
+    if (!p.pdl_late_wait) grid_dep_wait();
     if (tid < NQ) {
         u64 seed = 0ull;
         if (p.seed_keys != nullptr && tid < p.nq_valid) seed = p.seed_keys[p.q_begin + tid];
@@ -197,6 +201,8 @@ scan_topk_kernel(const ScanParams p) {
         __syncwarp();
     }
     __syncthreads();
+    grid_dep_launch();                          // the merge kernel may be scheduled: its launch latency hides here
+    if (p.pdl_late_wait) grid_dep_wait();       // the previous call's merge has finished reading the lists
 
     // final: leave exactly min(count, k) best keys per query, then publish
     for (int q = warp; q < NQ; q += kScanWarps) {

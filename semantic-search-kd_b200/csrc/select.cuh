@@ -68,6 +68,13 @@ __device__ __forceinline__ void st_u64_if(u64* ptr, u64 v, bool pred) {
         : "memory");
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream is still running; it must execute
+// grid_dep_wait() before touching anything the predecessor writes (or, for buffers the predecessor
+// READS, before overwriting them).  grid_dep_launch() lets the successor start early.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // In-place bitonic sort, DESCENDING, of a[0..n) (n a power of two, n/2 a multiple of nthreads)
 // by `nthreads` cooperating threads with ids tid in [0, nthreads).  `sync` is __syncwarp or
 // __syncthreads.  Compare-exchange is select + unconditional stores.

@@ -389,3 +389,35 @@ def test_tensor_other_dims(pkg, oracle):
         rep = oracle.compare_topk(D, I, Dr, Ir, Xb, Qb, tie_tol=TIE_TOL_F32)
         assert rep["ok"], (d, rep)
         idx.close()
+
+
+@pytest.mark.parametrize("k", [10, 100])
+def test_pdl_overlap_mode_back_to_back(pkg, oracle, k):
+    """Option pdl=2: the scan of call i+1 runs while the merge of call i still reads the shared
+    candidate workspace; 200 back-to-back device calls must give exactly the serialised answers."""
+    import torch
+    X = unit_rows(300000, 384, 71)
+    dev = torch.device("cuda", 0)
+    idx = build(pkg, X, path=1)
+    Q = torch.from_numpy(unit_rows(200, 384, 72)).to(dev)
+    ref_s, ref_i = [], []
+    for i in range(200):
+        s, ids = idx.search_device(Q[i:i + 1], k)
+        ref_s.append(s.clone())
+        ref_i.append(ids.clone())
+    torch.cuda.synchronize()
+    for mode in (2, 0):
+        idx.set_option("pdl", mode)
+        outs = [(torch.empty((1, k), dtype=torch.float32, device=dev), torch.empty((1, k), dtype=torch.int64, device=dev))
+                for _ in range(200)]
+        for i in range(200):
+            idx.search_device(Q[i:i + 1], k, out=outs[i])
+        torch.cuda.synchronize()
+        for i in range(200):
+            assert torch.equal(outs[i][1], ref_i[i]), (mode, i)
+            assert torch.equal(outs[i][0], ref_s[i]), (mode, i)
+    idx.set_option("pdl", 1)
+    D, I = idx.search(Q[:4].cpu().numpy(), k)
+    Dr, Ir = oracle.flat_ip_topk(X, Q[:4].cpu().numpy(), k)
+    assert oracle.compare_topk(D, I, Dr, Ir, X, Q[:4].cpu().numpy(), tie_tol=TIE_TOL_BF16)["ok"]
+    idx.close()
