@@ -109,10 +109,12 @@ struct b2s_index {
                                   //    valid when the query buffer is not written by the kernel enqueued
                                   //    immediately before the search on the same stream
     int opt_tc_sample_div = 0;    // the threshold pre-pass samples 1 / this of the full tiles (0 = by k)
+    int opt_tc_shared_thr = 1;    // tensor path: tighten thresholds through a per-query survivor histogram
+    int opt_tc_thr_period_ns = 10000;   // refresh period of the bound-updater warp
     int opt_tc_chunk_lo = 48;     // tiles per work item when several query blocks share the corpus
     int opt_tc_chunk_hi = 96;
     // workspace
-    DevBuf ws_lists, ws_counts, ws_thr, ws_gmax, ws_seed, ws_qf32, ws_qbf16, ws_io_q, ws_io_scores, ws_io_ids, ws_tmp;
+    DevBuf ws_lists, ws_counts, ws_thr, ws_gmax, ws_hist, ws_hcfg, ws_seed, ws_qf32, ws_qbf16, ws_io_q, ws_io_scores, ws_io_ids, ws_tmp;
     void* pin_q = nullptr;
     void* pin_out = nullptr;
     size_t pin_q_bytes = 0, pin_out_bytes = 0;
@@ -540,6 +542,8 @@ B2S_API int b2s_destroy(b2s_index* idx) {
     idx->ws_seed.release();
     idx->ws_thr.release();
     idx->ws_gmax.release();
+    idx->ws_hist.release();
+    idx->ws_hcfg.release();
     idx->ws_qf32.release();
     idx->ws_qbf16.release();
     idx->ws_io_q.release();
@@ -692,6 +696,10 @@ B2S_API int b2s_set_option(b2s_index* idx, const char* name, int64_t value) {
         g_pdl_enabled = value != 0;
     } else if (s == "tc_sample_div") {
         idx->opt_tc_sample_div = (int)std::min<int64_t>(1 << 20, std::max<int64_t>(0, value));
+    } else if (s == "tc_shared_thr") {
+        idx->opt_tc_shared_thr = value ? 1 : 0;
+    } else if (s == "tc_thr_period_ns") {
+        idx->opt_tc_thr_period_ns = (int)std::min<int64_t>(1000000, std::max<int64_t>(100, value));
     } else if (s == "tc_chunk_tiles") {
         if (value < 1 || value > 4096) return fail(B2S_ERR_INVALID, "tc_chunk_tiles must be in [1, 4096]");
         idx->opt_tc_chunk_lo = idx->opt_tc_chunk_hi = (int)value;
@@ -713,6 +721,7 @@ B2S_API int64_t b2s_get_option(const b2s_index* idx, const char* name) {
     if (s == "tc_min_nq") return idx->opt_tc_min_nq;
     if (s == "pdl") return idx->opt_pdl;
     if (s == "tc_sample_div") return idx->opt_tc_sample_div;
+    if (s == "tc_shared_thr") return idx->opt_tc_shared_thr;
     if (s == "tc_chunk_tiles") return idx->opt_tc_chunk_lo == idx->opt_tc_chunk_hi ? idx->opt_tc_chunk_lo : 0;
     if (s == "num_sms") return idx->num_sms;
     return -1;

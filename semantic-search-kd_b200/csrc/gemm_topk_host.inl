@@ -87,7 +87,7 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
         // Sample density by k (measured at 1024 queries x 8.8M rows, sweep in profiles/): the pre-pass costs
         // 1/div of a main pass, the survivors that take the epilogue's slow path number ~ k * div.
         const int div = idx->opt_tc_sample_div > 0 ? idx->opt_tc_sample_div
-                                                   : (k <= 25 ? 64 : (k <= 50 ? 32 : (k <= 150 ? 16 : 8)));
+                                                   : (idx->opt_tc_shared_thr ? 64 : (k <= 25 ? 64 : (k <= 50 ? 32 : (k <= 150 ? 16 : 8))));
         const int want_groups = std::max(1024, 8 * k);
         int ts = std::max((tiles_full + div - 1) / div,
                           (want_groups + kTcGroupsPerTile - 1) / kTcGroupsPerTile);
@@ -125,6 +125,11 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
         if ((rc = idx->ws_thr.ensure(n_state * sizeof(u64))) != B2S_OK) return rc;
         if ((rc = idx->ws_seed.ensure((size_t)nq_pad * sizeof(u64))) != B2S_OK) return rc;
         if (sample_tiles > 0 && (rc = idx->ws_gmax.ensure((size_t)nq_pad * groups * sizeof(float))) != B2S_OK) return rc;
+        // shared-threshold state: [hist nq_pad*64 | gthr nq_pad] u32 (zeroed per call) + hcfg
+        const bool shared_thr = sample_tiles > 0 && idx->opt_tc_shared_thr != 0;
+        const size_t hist_words = (size_t)nq_pad * (kTcHistBins + 1);
+        if (shared_thr && (rc = idx->ws_hist.ensure(hist_words * sizeof(unsigned))) != B2S_OK) return rc;
+        if (shared_thr && (rc = idx->ws_hcfg.ensure((size_t)nq_pad * sizeof(uint2))) != B2S_OK) return rc;
 
         TcParams p;
         memset(&p, 0, sizeof(p));
@@ -153,8 +158,9 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
             pp.groups = groups;
             gemm_topk_kernel<true><<<grid, kTcThreads, L.total + 1024, s>>>(tc.corpus_map, qmap, pp);
             CUDA_TRY(cudaGetLastError());
-            seed_select_kernel<<<(unsigned)nq_pad, kSeedThreads, 0, s>>>(pp.gmax, groups, k,
-                                                                         reinterpret_cast<u64*>(idx->ws_seed.p));
+            seed_select_kernel<<<(unsigned)nq_pad, kSeedThreads, 0, s>>>(
+                pp.gmax, groups, k, reinterpret_cast<u64*>(idx->ws_seed.p),
+                shared_thr ? reinterpret_cast<uint2*>(idx->ws_hcfg.p) : nullptr);
             CUDA_TRY(cudaGetLastError());
             idx->stats.kernel_launches += 2;
             p.seed_keys = reinterpret_cast<const u64*>(idx->ws_seed.p);
@@ -162,6 +168,13 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
 
         CUDA_TRY(cudaMemsetAsync(idx->ws_counts.p, 0, n_state * sizeof(int), s));
         CUDA_TRY(cudaMemsetAsync(idx->ws_thr.p, 0, n_state * sizeof(u64), s));
+        if (shared_thr) {
+            CUDA_TRY(cudaMemsetAsync(idx->ws_hist.p, 0, hist_words * sizeof(unsigned), s));
+            p.hcfg = reinterpret_cast<const uint2*>(idx->ws_hcfg.p);
+            p.hist = reinterpret_cast<unsigned*>(idx->ws_hist.p);
+            p.gthr = p.hist + (size_t)nq_pad * kTcHistBins;
+            p.hstep = idx->opt_tc_thr_period_ns;
+        }
         p.tiles_total = tiles_all;
         p.tile_mul = 1;
         p.chunk_tiles = qblocks > 1 ? tc_pick_chunk(tiles_all, qblocks, pairs, idx->opt_tc_chunk_lo, idx->opt_tc_chunk_hi)

@@ -54,6 +54,8 @@ constexpr int kTcQBlockBytes = kTcQueriesPerCta * kTcKBlock * 2;  // 16 KB per k
 constexpr int kTcMaxStages = 10;
 constexpr int kTcAccStages = 2;
 constexpr int kTcGroupsPerTile = kTcTileRows / 32;   // 32-row groups whose maxima the pre-pass records
+constexpr int kTcQbDone = -3;                        // s_cur_qb value: the epilogue has finished
+constexpr int kTcHistBins = 64;                      // score bins of the shared per-query survivor histogram
 
 struct TcParams {
     uint32_t n_rows;        // rows in the shard
@@ -75,6 +77,11 @@ struct TcParams {
     u64* thr_keys;          // [2 * pairs, nq_pad]   (zeroed by the host before the main pass)
     float* gmax;            // pre-pass out: [nq_pad, groups] maxima of 32-row groups
     int groups;             // tiles_total * 8 (pre-pass)
+    // shared per-query threshold tightening (main pass, only with a pre-pass): see hist_publish()
+    const uint2* hcfg;      // [nq_pad] {base ord, shift} from seed_select_kernel (shift > 31: disabled)
+    unsigned* hist;         // [nq_pad, kTcHistBins] survivors per score bin     (zeroed by the host)
+    unsigned* gthr;         // [nq_pad] ord of the best proven lower bound of the k-th score (zeroed)
+    int hstep;              // refresh period of the bound-updater warp, ns
 };
 
 // dynamic shared memory carve-up (all offsets from a 1024-byte aligned base; identical in both CTAs)
@@ -119,6 +126,37 @@ __device__ __noinline__ u64 list_keep_top_k(u64* a, int n, int k) {
     return m;
 }
 
+// Shared per-query threshold tightening.  Every survivor of query q (appended by some thread of some
+// CTA pair) is counted in the query's global histogram: bins of 2^shift score images above the
+// pre-pass bound `base` (one fire-and-forget RED per survivor).  The lower edge of the highest bin
+// b such that bins >= b hold at least k rows is a proven lower bound of the k-th best score (k
+// distinct corpus rows reach it); an otherwise idle warp of every CTA re-derives it for the
+// queries its CTA currently works on and publishes it with atomicMax, the epilogue threads pick it
+// up once per tile.  Counts only grow and stale reads under-count, so the bound is always valid;
+// thresholds then track the k-th best of ALL rows seen so far by the whole GPU instead of staying
+// at the pre-pass sample's.
+__device__ __forceinline__ void hist_count(unsigned* h, uint32_t ord, uint2 cfg) {
+    uint32_t bin = (ord - cfg.x) >> cfg.y;
+    bin = bin > (uint32_t)(kTcHistBins - 1) ? (uint32_t)(kTcHistBins - 1) : bin;
+    atomicAdd(h + bin, 1u);   // result unused: RED
+}
+// 0 = no bound better than the pre-pass one
+__device__ __forceinline__ uint32_t hist_bound(const unsigned* h, unsigned k, uint2 cfg) {
+    const uint4* hv = reinterpret_cast<const uint4*>(h);
+    unsigned acc = 0;
+    int bsel = 0;
+    bool found = false;
+#pragma unroll
+    for (int i = kTcHistBins / 4 - 1; i >= 0; --i) {
+        const uint4 v = __ldcg(hv + i);
+        acc += v.w; if (!found && acc >= k) { found = true; bsel = 4 * i + 3; }
+        acc += v.z; if (!found && acc >= k) { found = true; bsel = 4 * i + 2; }
+        acc += v.y; if (!found && acc >= k) { found = true; bsel = 4 * i + 1; }
+        acc += v.x; if (!found && acc >= k) { found = true; bsel = 4 * i; }
+    }
+    return (found && bsel > 0) ? cfg.x + ((uint32_t)bsel << cfg.y) : 0u;
+}
+
 template <bool PREPASS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_constant__ CUtensorMap map_queries,
@@ -137,6 +175,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
     uint64_t* acc_full = q_empty + 1;                 // [2]       per CTA (multicast commit)
     uint64_t* acc_empty = acc_full + kTcAccStages;    // [2]       leader: 16 epilogue warps arrive
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + kTcAccStages);
+    int* s_cur_qb = reinterpret_cast<int*>(s_tmem + 1);   // query block the epilogue works on (updater warp)
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -165,6 +204,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
         }
         ptx::fence_barrier_init();
     }
+    if (tid == 0) *s_cur_qb = -1;
     if (warp == 2) {
         ptx::tmem_alloc_pair(s_tmem, 512);
         ptx::tmem_relinquish_pair();
@@ -262,6 +302,44 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
                 if (reload_q) ptx::umma_commit_pair(q_empty);       // the query block may be overwritten
             }
         }
+    } else if (warp == 3) {
+        // ================= bound updater (see hist_bound) =================
+        if constexpr (!PREPASS) {
+            if (p.hcfg != nullptr) {
+                int last_qb = -1;
+                uint2 hc[4];
+                uint32_t pub[4];
+                while (true) {
+                    const int qb = *(volatile int*)s_cur_qb;
+                    if (qb == kTcQbDone) break;
+                    if (qb < 0) {
+                        __nanosleep(2000);
+                        continue;
+                    }
+                    if (qb != last_qb) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int q = qb * kTcQueriesPerPair + (int)rank * kTcQueriesPerCta + j * 32 + lane;
+                            hc[j] = q < p.nq ? p.hcfg[q] : make_uint2(0u, 0xffffffffu);
+                            pub[j] = 0u;
+                        }
+                        last_qb = qb;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int q = qb * kTcQueriesPerPair + (int)rank * kTcQueriesPerCta + j * 32 + lane;
+                        if (hc[j].y < 32u) {
+                            const uint32_t b = hist_bound(p.hist + (size_t)q * kTcHistBins, (unsigned)p.k, hc[j]);
+                            if (b > pub[j]) {
+                                atomicMax(p.gthr + q, b);
+                                pub[j] = b;
+                            }
+                        }
+                    }
+                    __nanosleep(p.hstep);   // refresh period (ns)
+                }
+            }
+        }
     } else if (warp >= 4) {
         // ================= epilogue: one thread <-> one query =================
         const int qt = warp & 3;                  // TMEM lane quarter this warp may read
@@ -291,11 +369,33 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
                     tk = ~0ull;
                 }
             }
+            uint2 hc = make_uint2(0u, 0xffffffffu);
+            if constexpr (!PREPASS) {
+                if (p.hcfg != nullptr && q < p.nq) hc = p.hcfg[q];
+            }
+            const bool shared_thr = hc.y < 32u;
+            unsigned* gthr_q = shared_thr ? p.gthr + q : nullptr;
+            unsigned* hist_q = shared_thr ? p.hist + (size_t)q * kTcHistBins : nullptr;
+            if (warp == 4 && lane == 0) *(volatile int*)s_cur_qb = qb;   // tell the bound-updater warp
             const int t0 = chunk * p.chunk_tiles;
             const int t1 = min(t0 + p.chunk_tiles, p.tiles_total);
             for (int t = t0; t < t1; ++t) {
+                // the query's shared bound (other CTA pairs raise it); the load flies during the wait
+                unsigned g = 0u;
+                if constexpr (!PREPASS) {
+                    if (shared_thr) g = __ldcg(gthr_q);
+                }
                 ptx::mbar_wait(&acc_full[acc], acc_phase);
                 ptx::tc_fence_after();
+                if constexpr (!PREPASS) {
+                    if (g != 0u) {
+                        const u64 gk = ((u64)g << 32) - 1ull;   // every score whose image is >= g passes
+                        if (gk > tk) {
+                            tk = gk;
+                            thr = key_score(tk);
+                        }
+                    }
+                }
                 const uint32_t col0 = (uint32_t)(acc * kTcTileRows + half * 128);
                 const uint32_t row_base = (uint32_t)(t * p.tile_mul) * kTcTileRows + (uint32_t)half * 128u;
 #pragma unroll 1
@@ -330,6 +430,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
                                             const u64 key = make_key(v[j], row);
                                             if (key > tk && row < p.n_rows) {
                                                 my_list[cnt++] = key;
+                                                if (shared_thr) hist_count(hist_q, (uint32_t)(key >> 32), hc);
                                                 if (cnt == p.cap) {
                                                     tk = list_keep_top_k(my_list, cnt, p.k);
                                                     thr = key_score(tk);
@@ -361,6 +462,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
         }
     }
 
+    if (warp == 4 && lane == 0) *(volatile int*)s_cur_qb = kTcQbDone;
+
     // ---- teardown ---------------------------------------------------------------------------
     ptx::tc_fence_before();
     __syncthreads();
@@ -376,17 +479,23 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
 // One CTA per query: MSB-first 8-bit radix select on the order-preserving integer image.
 constexpr int kSeedThreads = 256;
 __global__ void __launch_bounds__(kSeedThreads) seed_select_kernel(const float* __restrict__ gmax, int groups, int k,
-                                                                   u64* __restrict__ seed_keys) {
+                                                                   u64* __restrict__ seed_keys,
+                                                                   uint2* __restrict__ hcfg) {
     __shared__ int hist[256];
     __shared__ uint32_t s_prefix;
     __shared__ int s_rem;
+    __shared__ uint32_t s_max;
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
     const float* g = gmax + (size_t)q * groups;
     if (groups < k) {
-        if (tid == 0) seed_keys[q] = 0ull;
+        if (tid == 0) {
+            seed_keys[q] = 0ull;
+            if (hcfg) hcfg[q] = make_uint2(0u, 0xffffffffu);
+        }
         return;
     }
+    if (tid == 0) s_max = 0u;
     if (tid == 0) {
         s_prefix = 0u;
         s_rem = k;
@@ -399,6 +508,7 @@ __global__ void __launch_bounds__(kSeedThreads) seed_select_kernel(const float* 
         const uint32_t prefix = s_prefix;
         for (int i = tid; i < groups; i += kSeedThreads) {
             const uint32_t o = score_to_ord(g[i]);
+            if (pass == 0) atomicMax(&s_max, o);
             const bool in = pass == 0 || (o >> (shift + 8)) == (prefix >> (shift + 8));
             if (in) atomicAdd(&hist[(o >> shift) & 255u], 1);
         }
@@ -415,7 +525,17 @@ __global__ void __launch_bounds__(kSeedThreads) seed_select_kernel(const float* 
         __syncthreads();
     }
     // s_prefix = ord of the k-th largest maximum T; every score >= T must pass: key > (ord << 32) - 1
-    if (tid == 0) seed_keys[q] = s_prefix ? (((u64)s_prefix << 32) - 1ull) : 0ull;
+    if (tid == 0) {
+        seed_keys[q] = s_prefix ? (((u64)s_prefix << 32) - 1ull) : 0ull;
+        if (hcfg) {
+            // histogram geometry for the main pass: bins of 2^shift images from T up, the sample's best
+            // score lands in bin <= 61; anything above goes to the last bin
+            const uint32_t range = s_max - s_prefix;
+            uint32_t sh = 0;
+            while ((range >> sh) > (uint32_t)(kTcHistBins - 3)) ++sh;
+            hcfg[q] = s_prefix ? make_uint2(s_prefix, sh) : make_uint2(0u, 0xffffffffu);
+        }
+    }
 }
 
 // Host-side state of the tensor path kept in the index handle.

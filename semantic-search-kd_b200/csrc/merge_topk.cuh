@@ -187,62 +187,80 @@ __device__ __forceinline__ int merge_lists_sorted(const MergeParams& p, const in
         __syncthreads();
         m_sorted = C;
         sorted_done = true;
-    } else if (M <= kMergeSortCap) {
-        m_sorted = M;   // buf already holds every candidate
     } else {
-        if (tid == 0) s_fill = 0;
-        // MSB-first radix select of the k-th largest key
-        if (tid == 0) {
-            s_prefix = 0ull;
-            s_bits_done = 0;
-            s_k_rem = p.k;
-            s_bucket_cnt = M;
-        }
-        __syncthreads();
-        while (true) {
-            const int bits_done = s_bits_done;
-            const int k_rem = s_k_rem;
-            // stop when winners (k - k_rem) + bucket fit the sort buffer, or all bits are fixed
-            if ((p.k - k_rem) + s_bucket_cnt <= kMergeSortCap || bits_done >= 64) break;
-            const int nbits = (64 - bits_done) < kRadixBits ? (64 - bits_done) : kRadixBits;
-            const int shift = 64 - bits_done - nbits;
-            const u64 prefix = s_prefix;
-            for (int i = tid; i < kRadixBins; i += kMergeThreads) hist[i] = 0;
+        // Too many survivors for the rank sort: MSB-first radix select of the k-th largest key, then
+        // only the winners and the bucket that holds the k-th are sorted (~k keys, not all M).
+        const bool in_smem = M <= kMergeSortCap;   // buf[0..M) holds every candidate
+        int stop_cap = 2 * next_pow2(p.k);
+        stop_cap = stop_cap < 512 ? 512 : (stop_cap > kMergeSortCap ? kMergeSortCap : stop_cap);
+        if (in_smem && M <= stop_cap) {
+            m_sorted = M;
+        } else {
+            if (tid == 0) {
+                s_fill = 0;
+                s_prefix = 0ull;
+                s_bits_done = 0;
+                s_k_rem = p.k;
+                s_bucket_cnt = M;
+            }
             __syncthreads();
+            while (true) {
+                const int bits_done = s_bits_done;
+                const int k_rem = s_k_rem;
+                // stop when winners (k - k_rem) + bucket are few enough to sort, or all bits are fixed
+                if ((p.k - k_rem) + s_bucket_cnt <= stop_cap || bits_done >= 64) break;
+                const int nbits = (64 - bits_done) < kRadixBits ? (64 - bits_done) : kRadixBits;
+                const int shift = 64 - bits_done - nbits;
+                const u64 prefix = s_prefix;
+                for (int i = tid; i < kRadixBins; i += kMergeThreads) hist[i] = 0;
+                __syncthreads();
+                for (int e = tid; e < M; e += kMergeThreads) {
+                    const u64 key = in_smem ? buf[e] : fetch_candidate(p, offs, L, q, e);
+                    const bool in_bucket = bits_done == 0 || (key >> (64 - bits_done)) == prefix;
+                    if (in_bucket) atomicAdd(&hist[(int)((key >> shift) & ((1u << nbits) - 1u))], 1);
+                }
+                __syncthreads();
+                if (tid < 32) {
+                    // warp 0: lane l owns bins [32 l, 32 l + 32); suffix sums over lanes find the lane
+                    // in which the count from the top reaches k_rem, that lane walks its 32 bins
+                    int mine = 0;
+                    for (int b = 0; b < 32; ++b) mine += hist[tid * 32 + b];
+                    int above = 0;   // candidates in bins of higher lanes
+                    for (int l = 31; l >= 0; --l) {
+                        const int v = __shfl_sync(0xffffffffu, mine, l);
+                        if (l > tid) above += v;
+                    }
+                    const bool here = above < k_rem && above + mine >= k_rem;   // exactly one lane
+                    if (here) {
+                        int acc = above;
+                        int b = tid * 32 + 31;
+                        for (; b > tid * 32; --b) {
+                            if (acc + hist[b] >= k_rem) break;
+                            acc += hist[b];
+                        }
+                        // bucket b holds the k_rem-th largest of the current bucket
+                        s_prefix = (prefix << nbits) | (u64)b;
+                        s_bits_done = bits_done + nbits;
+                        s_k_rem = k_rem - acc;
+                        s_bucket_cnt = hist[b];
+                    }
+                }
+                __syncthreads();
+            }
+            // gather winners (prefix bits above the bucket) and the bucket itself
+            const int bits_done = s_bits_done;
+            const u64 prefix = s_prefix;
             for (int e = tid; e < M; e += kMergeThreads) {
                 const u64 key = fetch_candidate(p, offs, L, q, e);
-                const bool in_bucket = bits_done == 0 || (key >> (64 - bits_done)) == prefix;
-                if (in_bucket) atomicAdd(&hist[(int)((key >> shift) & ((1u << nbits) - 1u))], 1);
-            }
-            __syncthreads();
-            if (tid == 0) {
-                int acc = 0;
-                int b = (1 << nbits) - 1;
-                for (; b > 0; --b) {
-                    if (acc + hist[b] >= k_rem) break;
-                    acc += hist[b];
+                const bool take = bits_done == 0 || (key >> (64 - bits_done)) >= prefix;
+                if (take) {
+                    const int pos = atomicAdd(&s_fill, 1);
+                    if (pos < kMergeSortCap) buf[pos] = key;
                 }
-                // bucket b holds the k_rem-th largest of the current bucket
-                s_prefix = (prefix << nbits) | (u64)b;
-                s_bits_done = bits_done + nbits;
-                s_k_rem = k_rem - acc;
-                s_bucket_cnt = hist[b];
             }
             __syncthreads();
+            m_sorted = s_fill < kMergeSortCap ? s_fill : kMergeSortCap;
         }
-        // gather winners (prefix bits above the bucket) and the bucket itself
-        const int bits_done = s_bits_done;
-        const u64 prefix = s_prefix;
-        for (int e = tid; e < M; e += kMergeThreads) {
-            const u64 key = fetch_candidate(p, offs, L, q, e);
-            const bool take = bits_done == 0 || (key >> (64 - bits_done)) >= prefix;
-            if (take) {
-                const int pos = atomicAdd(&s_fill, 1);
-                if (pos < kMergeSortCap) buf[pos] = key;
-            }
-        }
-        __syncthreads();
-        m_sorted = s_fill < kMergeSortCap ? s_fill : kMergeSortCap;
     }
 
     if (!sorted_done) block_sort_desc(buf, m_sorted > 0 ? m_sorted : 1, tid);

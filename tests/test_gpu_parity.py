@@ -304,10 +304,23 @@ def test_ragged_sizes_tensor(pkg, oracle, n, nq):
 @pytest.mark.parametrize("k", [1, 10, 100, 200, 1000, 2048])
 def test_k_sweep_tensor(pkg, oracle, k):
     X, Q = unit_rows(40000, 384, 15), unit_rows(70, 384, 16)
-    for seed in (0, 1):
-        idx = build(pkg, X, path=2, seed=seed)
+    for seed, shared in ((0, 1), (1, 1), (1, 0)):
+        idx = build(pkg, X, path=2, seed=seed, tc_shared_thr=shared)
         check(oracle, idx, X, Q, k, q_bf16=True)
         idx.close()
+
+
+@pytest.mark.parametrize("k", [10, 100, 1000])
+def test_tensor_shared_threshold_large(pkg, oracle, k):
+    """The shared survivor histogram tightens thresholds across CTA pairs: sparse sample (1/64),
+    1M rows, several query blocks; must stay exact, also with near-duplicate-heavy data."""
+    X, Q = unit_rows(1000000, 384, 81), unit_rows(300, 384, 82)
+    X[5000:5400] = X[4999] + 1e-3 * unit_rows(400, 384, 83)      # a dense cluster of near ties
+    X[5000:5400] /= np.linalg.norm(X[5000:5400], axis=1, keepdims=True)
+    Q[0] = X[4999]
+    idx = build(pkg, X, path=2)
+    check(oracle, idx, X, Q, k, q_bf16=True)
+    idx.close()
 
 
 def test_tensor_ties_and_adversarial(pkg, oracle):
