@@ -125,11 +125,29 @@ def cpu_flat_qps(n_queries: int, warmup: int = 1):
     return 1.0 / per_query_full, info
 
 
-def cpu_hnsw_report(n=100_000, nq=1000):
+def cfg0_data(kind: str, n=100_000, nq=1000):
+    """BASELINE configs[0] inputs.  'isotropic' = i.i.d. Gaussian directions (the literal synthetic recipe,
+    tests/conftest.py:66-73 of the reference -- the worst case for any graph index: every point is almost
+    equidistant from every other); 'clustered' = a 48-dimensional latent mixture embedded in 384-d plus small
+    noise, queries = perturbed corpus rows (closer to what a text encoder produces)."""
+    from oracle import oracle as orc
+    if kind == "isotropic":
+        return orc.gen_unit_rows(n, DIM, 0), orc.gen_unit_rows(nq, DIM, 1)
+    rng = np.random.default_rng(1234)
+    proj = rng.standard_normal((48, DIM)).astype(np.float32) / np.sqrt(48)
+    centers = rng.standard_normal((256, 48)).astype(np.float32)
+    z = centers[rng.integers(0, 256, n)] + 0.6 * rng.standard_normal((n, 48)).astype(np.float32)
+    X = z @ proj + 0.05 * rng.standard_normal((n, DIM)).astype(np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    Q = X[rng.integers(0, n, nq)] + 0.05 * rng.standard_normal((nq, DIM)).astype(np.float32)
+    Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+    return np.ascontiguousarray(X, dtype=np.float32), np.ascontiguousarray(Q, dtype=np.float32)
+
+
+def cpu_hnsw_report(kind="isotropic", n=100_000, nq=1000):
     """BASELINE configs[0]: HNSW(32/200/64) restatement build + search + recall@10 vs flat, CPU."""
     from oracle import oracle as orc
-    X = orc.gen_unit_rows(n, DIM, 0)
-    Q = orc.gen_unit_rows(nq, DIM, 1)
+    X, Q = cfg0_data(kind, n, nq)
     t0 = time.perf_counter()
     h = orc.HnswRef(X, 32, 200)
     tb = time.perf_counter() - t0
@@ -139,11 +157,46 @@ def cpu_hnsw_report(n=100_000, nq=1000):
     t0 = time.perf_counter()
     _, If = orc.flat_ip_topk(X, Q, K, acc="f32")
     tf = time.perf_counter() - t0
-    return {"n": n, "nq": nq, "M": 32, "efConstruction": 200, "efSearch": 64, "build_s": round(tb, 2),
+    return {"data": kind, "n": n, "nq": nq, "M": 32, "efConstruction": 200, "efSearch": 64, "build_s": round(tb, 2),
             "hnsw_qps": round(nq / ts, 1), "flat_qps_batched": round(nq / tf, 1),
             "recall_at_10_vs_flat": round(orc.recall_at_k(Ih, If), 4), "cores": orc.num_threads(),
-            "note": "HNSW restatement (oracle/hnsw.cpp), not faiss; isotropic random 384-d data is the "
-                    "worst case for graph ANN"}
+            "note": "HNSW restatement (oracle/hnsw.cpp) with the reference's parameters (src/config.py:126-139), not faiss"}
+
+
+def gpu_cfg0_report(torch, pkg, dev, kinds=("isotropic", "clustered")):
+    """Our path on BASELINE configs[0] (100k x 384 fp32 rows, 1k queries, k=10): queries/s through the host
+    API and recall@10 against the CPU flat oracle (the checker) -- exact search, so 1.0 up to bf16 near-ties."""
+    from oracle import oracle as orc
+    out = []
+    for kind in kinds:
+        X, Q = cfg0_data(kind)
+        idx = pkg.FlatIPIndex(DIM, metric="inner_product", device=dev.index)
+        t0 = time.perf_counter()
+        idx.add(X)
+        torch.cuda.synchronize()
+        tb = time.perf_counter() - t0
+        idx.search(Q[:8], K)
+        t0 = time.perf_counter()
+        D, I = idx.search(Q, K)                       # one batched call (tensor path)
+        t_batch = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for i in range(200):
+            idx.search(Q[i:i + 1], K)                 # serving style, one query per call (scan path)
+        t_one = (time.perf_counter() - t0) / 200
+        Df, If = orc.flat_ip_topk(X, Q, K, acc="f32")
+        rep = orc.compare_topk(D, I, Df, If, X, Q, tie_tol=1e-3)
+        exact = pkg.FlatIPIndex(DIM, metric="inner_product", device=dev.index, keep_fp32=True)   # + fp32 re-ranking
+        exact.add(X)
+        _, Ie = exact.search(Q, K)
+        exact.close()
+        out.append({"data": kind, "n": len(X), "nq": len(Q), "build_s": round(tb, 3),
+                    "qps_one_batch_of_1000": round(len(Q) / t_batch, 1), "qps_batch1": round(1.0 / t_one, 1),
+                    "recall_at_10_vs_flat": round(orc.recall_at_k(I, If), 4),
+                    "recall_at_10_vs_flat_keep_fp32": round(orc.recall_at_k(Ie, If), 4),
+                    "ids_ok_under_parity_rule": rep["ok"],
+                    "tie_swaps": rep["tie_swaps"]})
+        idx.close()
+    return out
 
 
 def run_reference(args):
@@ -159,11 +212,14 @@ def run_reference(args):
             "cpu_baseline": dict(info, value=qps, unit="queries/s"),
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    if not args.no_hnsw:
-        try:
-            line["hnsw_cfg0"] = cpu_hnsw_report()
-        except Exception as e:  # never lose the main number
-            line["hnsw_cfg0"] = {"error": str(e)}
+    if not args.no_hnsw and args.gpus == 1:
+        # BASELINE configs[0], once per round (the N=1 run): the reference's HNSW configuration on the host cores
+        line["hnsw_cfg0"] = []
+        for kind in ("isotropic", "clustered"):
+            try:
+                line["hnsw_cfg0"].append(cpu_hnsw_report(kind))
+            except Exception as e:  # never lose the main number
+                line["hnsw_cfg0"].append({"data": kind, "error": str(e)})
     print(json.dumps(line), flush=True)
 
 
@@ -395,6 +451,10 @@ def run_ours(args):
                 line["cpu_baseline"] = dict(info, value=qps, unit="queries/s")
             except Exception as e:
                 line["cpu_baseline"] = {"error": str(e)}
+            try:
+                line["cfg0_recall"] = gpu_cfg0_report(torch, pkg, dev)
+            except Exception as e:
+                line["cfg0_recall"] = {"error": str(e)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -17,7 +17,7 @@ _ROOT = _PKG.parent
 _CSRC = _PKG / "csrc"
 _SO = _PKG / "libb200search.so"
 _SOURCES = ["b2s_api.cu", "select.cuh", "scan_topk.cuh", "merge_topk.cuh", "util_kernels.cuh",
-            "gemm_topk_tc.cuh", "gemm_topk_host.inl", "ptx.cuh", "ance_filter.cuh", "exchange.cuh"]
+            "gemm_topk_tc.cuh", "gemm_topk_host.inl", "ptx.cuh", "ance_filter.cuh", "exchange.cuh", "rescore.cuh"]
 
 B2S_OK = 0
 B2S_ERR_INVALID = -1

@@ -21,6 +21,7 @@
 #include "ance_filter.cuh"
 #include "exchange.cuh"
 #include "merge_topk.cuh"
+#include "rescore.cuh"
 #include "scan_topk.cuh"
 #include "select.cuh"
 #include "util_kernels.cuh"
@@ -114,7 +115,7 @@ struct b2s_index {
     int opt_tc_chunk_lo = 48;     // tiles per work item when several query blocks share the corpus
     int opt_tc_chunk_hi = 96;
     // workspace
-    DevBuf ws_lists, ws_counts, ws_thr, ws_gmax, ws_hist, ws_hcfg, ws_seed, ws_qf32, ws_qbf16, ws_io_q, ws_io_scores, ws_io_ids, ws_tmp;
+    DevBuf ws_lists, ws_counts, ws_thr, ws_gmax, ws_hist, ws_hcfg, ws_rs_scores, ws_rs_ids, ws_seed, ws_qf32, ws_qbf16, ws_io_q, ws_io_scores, ws_io_ids, ws_tmp;
     void* pin_q = nullptr;
     void* pin_out = nullptr;
     size_t pin_q_bytes = 0, pin_out_bytes = 0;
@@ -343,7 +344,7 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
 void tensor_path_release(b2s_index* idx);
 #endif
 
-int search_impl(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, int k, float* out_scores,
+int search_core(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, int k, float* out_scores,
                 int64_t* out_ids, cudaStream_t s) {
     if (!idx) return fail(B2S_ERR_INVALID, "null index");
     if (nq < 0 || k < 0) return fail(B2S_ERR_INVALID, "nq and k must be >= 0");
@@ -440,6 +441,29 @@ int search_impl(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, in
 #endif
     }
     if (idx->opt_timing) cudaEventRecord(idx->ev[3], s);
+    return B2S_OK;
+}
+
+// Search, then (option keep_f32) re-rank k + pad bf16 candidates with the fp32 copy of the rows: rescore.cuh.
+int search_impl(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, int k, float* out_scores,
+                int64_t* out_ids, cudaStream_t s) {
+    const bool rescore = idx && idx->opt_keep_f32 && idx->rows_f32 && idx->n > 0 && idx->ex_call == nullptr &&
+                         nq > 0 && k > 0 && k <= kMaxK && queries && out_scores && out_ids;
+    if (!rescore) return search_core(idx, queries, q_dtype, nq, k, out_scores, out_ids, s);
+    const int k2 = std::min(kRescoreCap, k + idx->opt_rescore_pad);
+    int rc;
+    if ((rc = use_device(idx)) != B2S_OK) return rc;
+    if ((rc = idx->ws_rs_scores.ensure((size_t)nq * k2 * sizeof(float))) != B2S_OK) return rc;
+    if ((rc = idx->ws_rs_ids.ensure((size_t)nq * k2 * sizeof(int64_t))) != B2S_OK) return rc;
+    float* cs = reinterpret_cast<float*>(idx->ws_rs_scores.p);
+    int64_t* ci = reinterpret_cast<int64_t*>(idx->ws_rs_ids.p);
+    if ((rc = search_core(idx, queries, q_dtype, nq, k2, cs, ci, s)) != B2S_OK) return rc;
+    rescore_f32_kernel<<<(unsigned)nq, kRescoreThreads, 0, s>>>(
+        idx->rows_f32, idx->n, idx->dim, queries, q_dtype == B2S_DTYPE_BF16, idx->metric == B2S_METRIC_COSINE ? 1 : 0, cs,
+        reinterpret_cast<const long long*>(ci), k2, idx->id_offset, k, out_scores, reinterpret_cast<long long*>(out_ids));
+    CUDA_TRY(cudaGetLastError());
+    idx->stats.kernel_launches++;
+    if (idx->opt_timing && idx->ev_valid) cudaEventRecord(idx->ev[3], s);
     return B2S_OK;
 }
 
@@ -543,6 +567,8 @@ B2S_API int b2s_destroy(b2s_index* idx) {
     idx->ws_thr.release();
     idx->ws_gmax.release();
     idx->ws_hist.release();
+    idx->ws_rs_scores.release();
+    idx->ws_rs_ids.release();
     idx->ws_hcfg.release();
     idx->ws_qf32.release();
     idx->ws_qbf16.release();
@@ -619,9 +645,14 @@ static int add_impl(b2s_index* idx, const void* rows, int64_t n, int is_device, 
                 reinterpret_cast<const float*>(dsrc), dst, rn, dim, normalize ? 1 : 0);
             CUDA_TRY(cudaGetLastError());
             if (idx->opt_keep_f32 && idx->rows_f32) {
-                // fp32 copy keeps the caller's values (normalised on the fly at re-score time if cosine)
+                // fp32 copy keeps the caller's values (unit-normalised for the cosine metric)
                 CUDA_TRY(cudaMemcpyAsync(idx->rows_f32 + (size_t)(idx->n + r0) * dim, dsrc,
                                          (size_t)rn * dim * sizeof(float), cudaMemcpyDeviceToDevice, idx->stream));
+                if (normalize) {
+                    rows_f32_normalize_kernel<<<blocks, warps * 32, 0, idx->stream>>>(
+                        idx->rows_f32 + (size_t)(idx->n + r0) * dim, rn, dim);
+                    CUDA_TRY(cudaGetLastError());
+                }
             }
         }
         CUDA_TRY(cudaStreamSynchronize(idx->stream));

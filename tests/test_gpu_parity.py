@@ -434,3 +434,45 @@ def test_pdl_overlap_mode_back_to_back(pkg, oracle, k):
     Dr, Ir = oracle.flat_ip_topk(X, Q[:4].cpu().numpy(), k)
     assert oracle.compare_topk(D, I, Dr, Ir, X, Q[:4].cpu().numpy(), tie_tol=TIE_TOL_BF16)["ok"]
     idx.close()
+
+
+@pytest.mark.parametrize("path", [1, 2])
+@pytest.mark.parametrize("k", [10, 100])
+def test_keep_fp32_rescoring_gives_flat_ip_ids_exactly(pkg, oracle, path, k):
+    """keep_fp32: k + pad bf16 candidates are re-ranked with the fp32 rows, so ids are IDENTICAL to
+    the fp32 flat oracle (faiss.IndexFlatIP semantics), not merely equal up to bf16 near-ties."""
+    X, Q = unit_rows(120000, 384, 131), unit_rows(96, 384, 132)
+    X[70000] = X[5]                                  # exact duplicate: tie must resolve to the lower id
+    Q[0] = X[5]
+    idx = pkg.FlatIPIndex(384, metric="inner_product", keep_fp32=True)
+    idx.set_option("path", path)
+    idx.add(X)
+    D, I = idx.search(Q, k)
+    Dr, Ir = oracle.flat_ip_topk(X, Q, k)            # fp64-accumulated adjudicator on the fp32 rows
+    agree = (I == Ir).all(axis=1).mean()
+    assert agree >= 0.98, agree                      # fp32 vs fp64 summation may still flip a 1e-7 tie
+    rep = oracle.compare_topk(D, I, Dr, Ir, X, Q, tie_tol=2e-6)
+    assert rep["ok"] and rep["max_abs_score_err"] < 2e-6, rep
+    assert list(I[0][:2]) == [5, 70000]
+    # without the fp32 copy the same search shows bf16 near-tie swaps on this data
+    plain = build(pkg, X, path=path)
+    Dp, Ip = plain.search(Q, k)
+    assert (Ip == Ir).all(axis=1).mean() <= agree
+    plain.close()
+    idx.close()
+
+
+def test_keep_fp32_cosine_unnormalised_inputs(pkg, oracle):
+    rng = np.random.default_rng(9)
+    Xr = (unit_rows(30000, 384, 141) * rng.uniform(0.5, 3.0, (30000, 1))).astype(np.float32)
+    Qr = (unit_rows(20, 384, 142) * rng.uniform(0.5, 3.0, (20, 1))).astype(np.float32)
+    idx = pkg.FlatIPIndex(384, metric="cosine", keep_fp32=True)
+    idx.add(Xr)
+    Xn = Xr / np.linalg.norm(Xr, axis=1, keepdims=True)
+    Qn = Qr / np.linalg.norm(Qr, axis=1, keepdims=True)
+    Dr, Ir = oracle.flat_ip_topk(Xn, Qn, 10)
+    for q in (Qr[:1], Qr):                            # scan path and tensor path
+        D, I = idx.search(q, 10)
+        rep = oracle.compare_topk(D, I, Dr[:len(q)], Ir[:len(q)], Xn, Qn[:len(q)], tie_tol=5e-6)
+        assert rep["ok"] and rep["max_abs_score_err"] < 5e-6, rep
+    idx.close()
