@@ -321,6 +321,7 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
             mp.counts = reinterpret_cast<const int*>(idx->ws_counts.p);
             mp.num_lists = grid;
             mp.nq_lists = chunk;
+            mp.lists_sorted = 1;   // scan_topk_kernel publishes sorted lists
             mp.cap = cap;
             mp.k = k;
             mp.id_offset = idx->id_offset;

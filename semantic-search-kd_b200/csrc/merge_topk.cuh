@@ -26,6 +26,7 @@ struct MergeParams {
     const int* counts;   // [L, nq_lists]
     int num_lists;       // L
     int nq_lists;        // list stride in queries
+    int lists_sorted;    // 1: every list is sorted descending (scan path) -> cheap merge without a gather
     int cap;
     int k;
     long long id_offset;  // added to decoded row ids
@@ -105,6 +106,68 @@ __device__ __forceinline__ int merge_lists_sorted(const MergeParams& p, const in
 
     const int tid = threadIdx.x;
     const int L = p.num_lists;    // host guarantees L <= kMergeMaxLists
+
+    if (p.lists_sorted) {
+        // ---- sorted lists (K1): the k-th largest list HEAD bounds the answer from below, and a sorted
+        // list can be cut at the first key under that floor: two dependent memory round trips in total,
+        // no prefix sum, no gather of every candidate.
+        u64* heads = reinterpret_cast<u64*>(hist);
+        for (int l = tid; l < kMergeMaxLists; l += kMergeThreads) {
+            int c = 0;
+            u64 h = 0ull;
+            if (l < L) {
+                c = p.counts[(size_t)l * p.nq_lists + q];
+                h = p.lists[((size_t)l * p.nq_lists + q) * p.cap];   // garbage when the list is empty
+            }
+            offs[l] = c;
+            heads[l] = c > 0 ? h : 0ull;
+        }
+        if (tid == 0) {
+            s_floor = 0ull;
+            s_nonempty = 0;
+            s_fill = 0;
+        }
+        __syncthreads();
+        {
+            int mine = 0;
+            for (int l = tid; l < L; l += kMergeThreads) mine += heads[l] != 0ull;
+            if (mine) atomicAdd(&s_nonempty, mine);
+        }
+        __syncthreads();
+        if (s_nonempty >= p.k) {
+            for (int l = tid; l < L; l += kMergeThreads) {
+                const u64 h = heads[l];
+                int rank = 0;
+                for (int j = 0; j < L; ++j) rank += heads[j] > h;
+                if (rank == p.k - 1 && h != 0ull) s_floor = h;   // keys are unique: exactly one writer
+            }
+        }
+        __syncthreads();
+        const u64 floor_key = s_floor;
+        for (int l = tid; l < L; l += kMergeThreads) {
+            const int c = offs[l];
+            const u64* lp = p.lists + ((size_t)l * p.nq_lists + q) * p.cap;
+            u64 key = heads[l];
+            for (int i = 0; i < c && key >= floor_key; ) {
+                const int pos = atomicAdd(&s_fill, 1);
+                if (pos < kMergeFastCap) sel[pos] = key;
+                if (++i < c) key = lp[i];
+            }
+        }
+        __syncthreads();
+        const int C = s_fill;
+        if (C <= kMergeFastCap) {
+            for (int t = tid; t < C; t += kMergeThreads) {
+                const u64 key = sel[t];
+                int rank = 0;
+                for (int j = 0; j < C; ++j) rank += sel[j] > key;
+                buf[rank] = key;
+            }
+            __syncthreads();
+            return C;
+        }
+        __syncthreads();   // too many survivors (many ties / tiny k-th bound): the general path below
+    }
 
     // exclusive prefix sums of the per-list counts (Hillis-Steele in shared memory)
     for (int l = tid; l < L; l += kMergeThreads) offs[l + 1] = p.counts[(size_t)l * p.nq_lists + q];

@@ -204,11 +204,10 @@ scan_topk_kernel(const ScanParams p) {
     grid_dep_launch();                          // the merge kernel may be scheduled: its launch latency hides here
     if (p.pdl_late_wait) grid_dep_wait();       // the previous call's merge has finished reading the lists
 
-    // final: leave exactly min(count, k) best keys per query, then publish
-    for (int q = warp; q < NQ; q += kScanWarps) {
-        if (*(volatile int*)&s_count[q] > p.k)
-            list_compact_warp(list_of(q), entries + (size_t)q * p.cap, p.cap, p.k, lane);
-    }
+    // final: leave exactly min(count, k) best keys per query, SORTED descending (the merge kernel
+    // relies on it: a list's first key is its maximum), then publish
+    for (int q = warp; q < NQ; q += kScanWarps)
+        list_compact_warp(list_of(q), entries + (size_t)q * p.cap, p.cap, p.k, lane);
     __syncthreads();
     for (int q = 0; q < p.nq_valid; ++q) {
         const int c = s_count[q];
