@@ -99,8 +99,12 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
     const int groups = sample_tiles * kTcGroupsPerTile;
     idx->stats.seeded = sample_tiles > 0 ? 1 : 0;
 
-    for (int64_t c0 = 0; c0 < nq; c0 += kTcQueryChunk) {
-        const int cn = (int)std::min<int64_t>(kTcQueryChunk, nq - c0);
+    // queries per workspace round: the candidate lists take 2*pairs * round * cap * 8 bytes (2.5 GB at
+    // 4096 queries and k <= 256); keep that bound for larger k by shrinking the round
+    int round_q = kTcQueryChunk;
+    while (round_q > kTcQueriesPerPair && (int64_t)round_q * cap > (int64_t)kTcQueryChunk * 512) round_q >>= 1;
+    for (int64_t c0 = 0; c0 < nq; c0 += round_q) {
+        const int cn = (int)std::min<int64_t>(round_q, nq - c0);
         const int qblocks = (cn + kTcQueriesPerPair - 1) / kTcQueriesPerPair;
         const int nq_pad = qblocks * kTcQueriesPerPair;
 
