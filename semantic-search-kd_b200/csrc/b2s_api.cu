@@ -112,6 +112,7 @@ struct b2s_index {
     int opt_tc_sample_div = 0;    // the threshold pre-pass samples 1 / this of the full tiles (0 = by k)
     int opt_tc_shared_thr = 1;    // tensor path: tighten thresholds through a per-query survivor histogram
     int opt_tc_thr_period_ns = 10000;   // refresh period of the bound-updater warp
+    int opt_tc_single_cta = 1;    // tensor path: single-CTA MMAs (M = 128) for batches of <= 128 queries
     int opt_tc_chunk_lo = 48;     // tiles per work item when several query blocks share the corpus
     int opt_tc_chunk_hi = 96;
     // workspace
@@ -732,6 +733,8 @@ B2S_API int b2s_set_option(b2s_index* idx, const char* name, int64_t value) {
         idx->opt_tc_shared_thr = value ? 1 : 0;
     } else if (s == "tc_thr_period_ns") {
         idx->opt_tc_thr_period_ns = (int)std::min<int64_t>(1000000, std::max<int64_t>(100, value));
+    } else if (s == "tc_single_cta") {
+        idx->opt_tc_single_cta = value ? 1 : 0;
     } else if (s == "tc_chunk_tiles") {
         if (value < 1 || value > 4096) return fail(B2S_ERR_INVALID, "tc_chunk_tiles must be in [1, 4096]");
         idx->opt_tc_chunk_lo = idx->opt_tc_chunk_hi = (int)value;

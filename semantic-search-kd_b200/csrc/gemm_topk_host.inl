@@ -19,9 +19,13 @@ int tc_init(b2s_index* idx) {
         CUDA_TRY(cudaDeviceGetAttribute(&tc.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, idx->device));
     }
     if (!tc.attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(gemm_topk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       tc.max_smem_optin));
-        CUDA_TRY(cudaFuncSetAttribute(gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(gemm_topk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      tc.max_smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(gemm_topk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      tc.max_smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(gemm_topk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       tc.max_smem_optin));
         tc.attr_set = true;
     }
@@ -38,6 +42,26 @@ int tc_encode_rows(b2s_index* idx, CUtensorMap* map, const void* base, uint64_t 
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(B2S_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
     return B2S_OK;
+}
+
+// K2 launch: 2-CTA clusters for the pair variant, plain grid for the single-CTA variant.
+template <bool PREPASS, bool PAIR>
+cudaError_t tc_launch(int ctas, size_t smem, cudaStream_t s, const CUtensorMap& corpus, const CUtensorMap& queries,
+                      const TcParams& p) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = PAIR ? 2 : 1;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_topk_kernel<PREPASS, PAIR>, corpus, queries, p);
 }
 
 // Tiles per work item in [lo, hi] that minimises the makespan (rounds x tiles) of dealing
@@ -66,9 +90,16 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
     const int kblocks = idx->dim / kTcKBlock;
     if (!tc.corpus_map_valid) {
         if ((rc = tc_encode_rows(idx, &tc.corpus_map, idx->rows, (uint64_t)idx->n, kTcRowsPerCta)) != B2S_OK) return rc;
+        if ((rc = tc_encode_rows(idx, &tc.corpus_map_full, idx->rows, (uint64_t)idx->n, kTcTileRows)) != B2S_OK) return rc;
         tc.corpus_map_valid = true;
     }
-    const int pairs = std::max(1, idx->num_sms / 2);
+    // <= 128 queries: every CTA on its own (M = 128); above: CTA pairs (M = 256).  "units" = work units.
+    const bool pair_mode = nq > kTcQueriesPerCta || idx->opt_tc_single_cta == 0;
+    const int qblock = pair_mode ? kTcQueriesPerPair : kTcQueriesPerCta;
+    const int pairs = pair_mode ? std::max(1, idx->num_sms / 2) : idx->num_sms;
+    const int ctas = pair_mode ? 2 * pairs : pairs;
+    const int stage_bytes = pair_mode ? kTcStageBytes : 2 * kTcStageBytes;
+    const CUtensorMap& corpus_map = pair_mode ? tc.corpus_map : tc.corpus_map_full;
     const int num_lists = 2 * pairs;
     if (num_lists > kMergeMaxLists) return fail(B2S_ERR_UNSUPPORTED, "too many SMs for the merge kernel");
     const int tiles_all = (int)((idx->n + kTcTileRows - 1) / kTcTileRows);
@@ -76,8 +107,8 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
 
     // pipeline depth from the shared-memory budget
     int stages = kTcMaxStages;
-    while (stages > 2 && (int)tc_smem_layout(kblocks, stages).total + 1024 > tc.max_smem_optin) --stages;
-    const TcSmemLayout L = tc_smem_layout(kblocks, stages);
+    while (stages > 2 && (int)tc_smem_layout(kblocks, stages, stage_bytes).total + 1024 > tc.max_smem_optin) --stages;
+    const TcSmemLayout L = tc_smem_layout(kblocks, stages, stage_bytes);
     if ((int)L.total + 1024 > tc.max_smem_optin)
         return fail(B2S_ERR_UNSUPPORTED, "tensor path: shared memory budget exceeded for this dim");
 
@@ -102,11 +133,11 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
     // queries per workspace round: the candidate lists take 2*pairs * round * cap * 8 bytes (2.5 GB at
     // 4096 queries and k <= 256); keep that bound for larger k by shrinking the round
     int round_q = kTcQueryChunk;
-    while (round_q > kTcQueriesPerPair && (int64_t)round_q * cap > (int64_t)kTcQueryChunk * 512) round_q >>= 1;
+    while (round_q > qblock && (int64_t)round_q * cap > (int64_t)kTcQueryChunk * 512) round_q >>= 1;
     for (int64_t c0 = 0; c0 < nq; c0 += round_q) {
         const int cn = (int)std::min<int64_t>(round_q, nq - c0);
-        const int qblocks = (cn + kTcQueriesPerPair - 1) / kTcQueriesPerPair;
-        const int nq_pad = qblocks * kTcQueriesPerPair;
+        const int qblocks = (cn + qblock - 1) / qblock;
+        const int nq_pad = qblocks * qblock;
 
         // queries -> bf16 [nq_pad, dim], zero padded, optionally normalised
         if ((rc = idx->ws_qbf16.ensure((size_t)nq_pad * idx->dim * 2)) != B2S_OK) return rc;
@@ -149,7 +180,6 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
         p.lists = reinterpret_cast<u64*>(idx->ws_lists.p);
         p.counts = reinterpret_cast<int*>(idx->ws_counts.p);
         p.thr_keys = reinterpret_cast<u64*>(idx->ws_thr.p);
-        const dim3 grid((unsigned)(2 * pairs), 1, 1);
 
         if (sample_tiles > 0) {
             TcParams pp = p;
@@ -160,8 +190,8 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
             pp.policy = ptx::kEvictNormal;
             pp.gmax = reinterpret_cast<float*>(idx->ws_gmax.p);
             pp.groups = groups;
-            gemm_topk_kernel<true><<<grid, kTcThreads, L.total + 1024, s>>>(tc.corpus_map, qmap, pp);
-            CUDA_TRY(cudaGetLastError());
+            if (pair_mode) CUDA_TRY((tc_launch<true, true>(ctas, L.total + 1024, s, corpus_map, qmap, pp)));
+            else CUDA_TRY((tc_launch<true, false>(ctas, L.total + 1024, s, corpus_map, qmap, pp)));
             seed_select_kernel<<<(unsigned)nq_pad, kSeedThreads, 0, s>>>(
                 pp.gmax, groups, k, reinterpret_cast<u64*>(idx->ws_seed.p),
                 shared_thr ? reinterpret_cast<uint2*>(idx->ws_hcfg.p) : nullptr);
@@ -185,8 +215,8 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
                                     : tc_pick_chunk(tiles_all, 1, pairs, 8, 32);
         p.num_chunks = (tiles_all + p.chunk_tiles - 1) / p.chunk_tiles;
         if (idx->opt_timing && c0 == 0) cudaEventRecord(idx->ev[1], s);
-        gemm_topk_kernel<false><<<grid, kTcThreads, L.total + 1024, s>>>(tc.corpus_map, qmap, p);
-        CUDA_TRY(cudaGetLastError());
+        if (pair_mode) CUDA_TRY((tc_launch<false, true>(ctas, L.total + 1024, s, corpus_map, qmap, p)));
+        else CUDA_TRY((tc_launch<false, false>(ctas, L.total + 1024, s, corpus_map, qmap, p)));
         idx->stats.kernel_launches++;
         idx->stats.passes += qblocks;
         if (idx->opt_timing && c0 == 0) cudaEventRecord(idx->ev[2], s);

@@ -88,11 +88,11 @@ struct TcParams {
 struct TcSmemLayout {
     uint32_t q_off, b_off, bar_off, total;
 };
-__host__ __device__ inline TcSmemLayout tc_smem_layout(int kblocks, int stages) {
+__host__ __device__ inline TcSmemLayout tc_smem_layout(int kblocks, int stages, int stage_bytes = kTcStageBytes) {
     TcSmemLayout L;
     L.q_off = 0;
     L.b_off = (uint32_t)kblocks * kTcQBlockBytes;
-    L.bar_off = L.b_off + (uint32_t)stages * kTcStageBytes;
+    L.bar_off = L.b_off + (uint32_t)stages * (uint32_t)stage_bytes;
     L.total = L.bar_off + 256;   // 2*10 + 2 + 4 barriers of 8 bytes + the TMEM base address
     return L;
 }
@@ -157,14 +157,22 @@ __device__ __forceinline__ uint32_t hist_bound(const unsigned* h, unsigned k, ui
     return (found && bsel > 0) ? cfg.x + ((uint32_t)bsel << cfg.y) : 0u;
 }
 
-template <bool PREPASS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+// PAIR = true : launched as 2-CTA clusters, one cta_group::2 MMA (M = 256 queries) per pair, each CTA
+//               stages 128 of the tile's 256 rows.  For batches above 128 queries.
+// PAIR = false: every CTA on its own (cta_group::1, M = 128 queries, it stages all 256 rows of its
+//               tiles): for <= 128 queries the second CTA of a pair would multiply padding, and the
+//               batch is HBM-bound anyway -- twice the tiles in flight per MMA cycle spent.
+template <bool PREPASS, bool PAIR>
+__global__ void __launch_bounds__(kTcThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_constant__ CUtensorMap map_queries,
                  const TcParams p) {
+    constexpr int kStageBytes = PAIR ? kTcStageBytes : 2 * kTcStageBytes;
+    constexpr int kQueriesPerBlock = PAIR ? kTcQueriesPerPair : kTcQueriesPerCta;
+    constexpr uint32_t kCtas = PAIR ? 2u : 1u;
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
     // SWIZZLE_128B tiles need a 1024-byte aligned base; the launch adds 1024 bytes of slack
     unsigned char* smem = tc_smem_raw + ((1024u - (ptx::smem_u32(tc_smem_raw) & 1023u)) & 1023u);
-    const TcSmemLayout L = tc_smem_layout(p.kblocks, p.stages);
+    const TcSmemLayout L = tc_smem_layout(p.kblocks, p.stages, kStageBytes);
     unsigned char* smem_q = smem + L.q_off;
     unsigned char* smem_b = smem + L.b_off;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
@@ -180,9 +188,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
-    const uint32_t rank = ptx::cluster_ctarank();     // 0 = leader
-    const int pair = blockIdx.x >> 1;
-    const int num_pairs = gridDim.x >> 1;
+    const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;     // 0 = leader
+    const int pair = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // index of this work unit (pair or CTA)
+    const int num_pairs = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int items_total = p.num_chunks * p.qblocks;
     const bool reload_q = p.qblocks > 1;
 
@@ -200,25 +208,30 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
         ptx::mbar_init(q_empty, 1);
         for (int i = 0; i < kTcAccStages; ++i) {
             ptx::mbar_init(&acc_full[i], 1);
-            ptx::mbar_init(&acc_empty[i], 2 * kTcEpiWarps);
+            ptx::mbar_init(&acc_empty[i], kCtas * kTcEpiWarps);
         }
         ptx::fence_barrier_init();
     }
     if (tid == 0) *s_cur_qb = -1;
     if (warp == 2) {
-        ptx::tmem_alloc_pair(s_tmem, 512);
-        ptx::tmem_relinquish_pair();
+        if constexpr (PAIR) {
+            ptx::tmem_alloc_pair(s_tmem, 512);
+            ptx::tmem_relinquish_pair();
+        } else {
+            ptx::tmem_alloc(s_tmem, 512);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    ptx::cluster_sync_all();   // the peer's barriers exist before anything is signalled on them
+    if constexpr (PAIR) ptx::cluster_sync_all();   // the peer's barriers exist before anything is signalled on them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
     if (warp == 0) {
         // ================= TMA producer (both CTAs; bytes are counted on the leader's barriers) ====
         if (lane == 0) {
-            const uint32_t q_full_leader = ptx::mapa_u32(ptx::smem_u32(q_full), 0);
+            const uint32_t q_full_leader = PAIR ? ptx::mapa_u32(ptx::smem_u32(q_full), 0) : ptx::smem_u32(q_full);
             int stage = 0;
             uint32_t phase = 0;
             uint32_t q_loads = 0;
@@ -227,11 +240,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
                 const int qb = item - chunk * p.qblocks;
                 if (reload_q || q_loads == 0) {
                     ptx::mbar_wait(q_empty, (q_loads & 1u) ^ 1u);   // MMAs that read the old block are done
-                    if (rank == 0) ptx::mbar_expect_tx(q_full, 2u * (uint32_t)p.kblocks * kTcQBlockBytes);
+                    if (rank == 0) ptx::mbar_expect_tx(q_full, kCtas * (uint32_t)p.kblocks * kTcQBlockBytes);
                     for (int kb = 0; kb < p.kblocks; ++kb)
-                        ptx::tma_load_2d_pair(smem_q + (size_t)kb * kTcQBlockBytes, &map_queries, q_full_leader,
-                                              kb * kTcKBlock, qb * kTcQueriesPerPair + (int)rank * kTcQueriesPerCta,
-                                              ptx::kEvictLast);
+                        ptx::tma_load_2d_on<PAIR>(smem_q + (size_t)kb * kTcQBlockBytes, &map_queries, q_full_leader,
+                                                  kb * kTcKBlock, qb * kQueriesPerBlock + (int)rank * kTcQueriesPerCta,
+                                                  ptx::kEvictLast);
                     ++q_loads;
                 }
                 const int t0 = chunk * p.chunk_tiles;
@@ -240,10 +253,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
                     const int row0 = t * p.tile_mul * kTcTileRows + (int)rank * kTcRowsPerCta;
                     for (int kb = 0; kb < p.kblocks; ++kb) {
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                        if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2u * kTcStageBytes);
-                        ptx::tma_load_2d_pair(smem_b + (size_t)stage * kTcStageBytes, &map_corpus,
-                                              ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0), kb * kTcKBlock, row0,
-                                              p.policy);
+                        if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], kCtas * kTcStageBytes * (PAIR ? 1u : 2u));
+                        const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
+                        ptx::tma_load_2d_on<PAIR>(smem_b + (size_t)stage * kStageBytes, &map_corpus,
+                                                  PAIR ? ptx::mapa_u32(fb, 0) : fb, kb * kTcKBlock, row0, p.policy);
                         if (++stage == p.stages) {
                             stage = 0;
                             phase ^= 1;
@@ -257,7 +270,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
     } else if (warp == 1) {
         // ================= MMA issuer (leader CTA, one lane) =================
         if (rank == 0 && lane == 0) {
-            const uint32_t idesc = ptx::idesc_bf16_f32(kTcQueriesPerPair, kTcTileRows);
+            const uint32_t idesc = ptx::idesc_bf16_f32(kQueriesPerBlock, kTcTileRows);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -280,26 +293,26 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
                         ptx::mbar_wait(&full_bar[stage], phase);
                         ptx::tc_fence_after();
                         const uint64_t da = ptx::smem_desc_sw128(ptx::smem_u32(smem_q + (size_t)kb * kTcQBlockBytes));
-                        const uint64_t db = ptx::smem_desc_sw128(ptx::smem_u32(smem_b + (size_t)stage * kTcStageBytes));
+                        const uint64_t db = ptx::smem_desc_sw128(ptx::smem_u32(smem_b + (size_t)stage * kStageBytes));
 #pragma unroll
                         for (int kk = 0; kk < kTcKBlock / 16; ++kk) {
                             // advance 16 elements = 32 bytes inside the 128-byte swizzle row: +2 (16-byte units)
-                            ptx::umma_bf16_pair(tmem_d, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc,
-                                                (uint32_t)((kb | kk) != 0));
+                            ptx::umma_bf16_on<PAIR>(tmem_d, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc,
+                                                    (uint32_t)((kb | kk) != 0));
                         }
-                        ptx::umma_commit_pair(&empty_bar[stage]);   // frees the stage in both CTAs
+                        ptx::umma_commit_on<PAIR>(&empty_bar[stage]);   // frees the stage (in both CTAs of a pair)
                         if (++stage == p.stages) {
                             stage = 0;
                             phase ^= 1;
                         }
                     }
-                    ptx::umma_commit_pair(&acc_full[acc]);          // accumulator tile complete (both CTAs)
+                    ptx::umma_commit_on<PAIR>(&acc_full[acc]);      // accumulator tile complete
                     if (++acc == kTcAccStages) {
                         acc = 0;
                         acc_phase ^= 1;
                     }
                 }
-                if (reload_q) ptx::umma_commit_pair(q_empty);       // the query block may be overwritten
+                if (reload_q) ptx::umma_commit_on<PAIR>(q_empty);   // the query block may be overwritten
             }
         }
     } else if (warp == 3) {
@@ -319,7 +332,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
                     if (qb != last_qb) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const int q = qb * kTcQueriesPerPair + (int)rank * kTcQueriesPerCta + j * 32 + lane;
+                            const int q = qb * kQueriesPerBlock + (int)rank * kTcQueriesPerCta + j * 32 + lane;
                             hc[j] = q < p.nq ? p.hcfg[q] : make_uint2(0u, 0xffffffffu);
                             pub[j] = 0u;
                         }
@@ -327,7 +340,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const int q = qb * kTcQueriesPerPair + (int)rank * kTcQueriesPerCta + j * 32 + lane;
+                        const int q = qb * kQueriesPerBlock + (int)rank * kTcQueriesPerCta + j * 32 + lane;
                         if (hc[j].y < 32u) {
                             const uint32_t b = hist_bound(p.hist + (size_t)q * kTcHistBins, (unsigned)p.k, hc[j]);
                             if (b > pub[j]) {
@@ -345,13 +358,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
         const int qt = warp & 3;                  // TMEM lane quarter this warp may read
         const int half = (warp - 4) >> 2;         // column half of the accumulator
         const uint32_t lane_addr = (uint32_t)(qt * 32) << 16;
-        const uint32_t acc_empty_leader0 = ptx::mapa_u32(ptx::smem_u32(&acc_empty[0]), 0);
+        const uint32_t acc_empty_leader0 = PAIR ? ptx::mapa_u32(ptx::smem_u32(&acc_empty[0]), 0) : ptx::smem_u32(&acc_empty[0]);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int item = pair; item < items_total; item += num_pairs) {
             const int chunk = item / p.qblocks;
             const int qb = item - chunk * p.qblocks;
-            const int q = qb * kTcQueriesPerPair + (int)rank * kTcQueriesPerCta + qt * 32 + lane;
+            const int q = qb * kQueriesPerBlock + (int)rank * kTcQueriesPerCta + qt * 32 + lane;
             const size_t list_id = (size_t)(pair * 2 + half) * p.nq_pad + q;
             // list state of (this pair, this column half, query q)
             u64* my_list = nullptr;
@@ -467,10 +480,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
     // ---- teardown ---------------------------------------------------------------------------
     ptx::tc_fence_before();
     __syncthreads();
-    ptx::cluster_sync_all();   // the peer no longer reads this CTA's shared memory / TMEM / barriers
+    if constexpr (PAIR) ptx::cluster_sync_all();   // the peer no longer reads this CTA's shared memory / TMEM / barriers
     if (warp == 2) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc_pair(tmem_base, 512);
+        if constexpr (PAIR) ptx::tmem_dealloc_pair(tmem_base, 512);
+        else ptx::tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -544,7 +558,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct TensorPathState {
-    CUtensorMap corpus_map;
+    CUtensorMap corpus_map;        // boxes of 128 rows (pair variant: each CTA stages half a tile)
+    CUtensorMap corpus_map_full;   // boxes of 256 rows (single-CTA variant)
     bool corpus_map_valid = false;
     PFN_encodeTiled encode = nullptr;
     int max_smem_optin = 0;

@@ -206,6 +206,32 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
         ::"r"(smem_u32(bar)), "h"((uint16_t)3)
         : "memory");
 }
+// PAIR-templated front ends: the same kernel body serves the 2-CTA and the single-CTA variant.
+// `bar_addr` is a shared::cluster address (a shared::cta address is valid as one for the own CTA).
+template <bool PAIR>
+__device__ __forceinline__ void tma_load_2d_on(void* smem_dst, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1,
+                                               uint64_t policy) {
+    if constexpr (PAIR) {
+        tma_load_2d_pair(smem_dst, m, bar_addr, c0, c1, policy);
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+            " [%0], [%1, {%3, %4}], [%2], %5;"
+            ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "l"(policy)
+            : "memory");
+    }
+}
+template <bool PAIR>
+__device__ __forceinline__ void umma_bf16_on(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    if constexpr (PAIR) umma_bf16_pair(tmem_d, desc_a, desc_b, idesc, accumulate);
+    else umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
+}
+template <bool PAIR>
+__device__ __forceinline__ void umma_commit_on(uint64_t* bar) {
+    if constexpr (PAIR) umma_commit_pair(bar);
+    else umma_commit(bar);
+}
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;  // default L2 policy (corpus tiles re-read by peers)
 
 // Shared-memory matrix descriptor, K-major operand tile whose rows are 128 bytes (64 bf16) and

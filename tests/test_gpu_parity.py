@@ -476,3 +476,16 @@ def test_keep_fp32_cosine_unnormalised_inputs(pkg, oracle):
         rep = oracle.compare_topk(D, I, Dr[:len(q)], Ir[:len(q)], Xn, Qn[:len(q)], tie_tol=5e-6)
         assert rep["ok"] and rep["max_abs_score_err"] < 5e-6, rep
     idx.close()
+
+
+@pytest.mark.parametrize("single", [0, 1])
+def test_tensor_small_batch_both_mma_shapes(pkg, oracle, single):
+    """<= 128 queries run as single-CTA MMAs (M = 128, option tc_single_cta=1, default) or as CTA pairs
+    with padding queries (0); both must agree with the oracle and with each other."""
+    X, Q = unit_rows(200000, 384, 151), unit_rows(100, 384, 152)
+    idx = build(pkg, X, path=2, tc_single_cta=single)
+    for nq, k in ((3, 10), (100, 10), (64, 100), (128, 300)):
+        q = np.concatenate([Q, Q[:28]])[:nq]
+        check(oracle, idx, X, q, k, q_bf16=True)
+        assert idx.stats()["path"] == 2
+    idx.close()
