@@ -142,6 +142,8 @@ struct b2s_index {
     } ex;
     const ExchangeArgs* ex_call = nullptr;
     int ex_fused = 0;
+    unsigned* done_counter = nullptr;   // device word for the scan kernel's fused merge tail
+    int opt_fused_tail = 1;
 #ifndef B2S_NO_TENSOR_PATH
     TensorPathState tc;
 #endif
@@ -220,7 +222,15 @@ template <int CPL, int NQ, int U>
 int launch_scan_t(const ScanParams& p, int grid, cudaStream_t s) {
     const size_t smem = (size_t)NQ * p.cap * sizeof(u64);
     auto kern = scan_topk_kernel<CPL, NQ, U>;
-    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // dynamic candidate lists sit next to ~44 KB of static shared memory (the fused merge tail): opt in
+    // once per instantiation for the largest list set (k = 2048: NQ * 4096 keys)
+    static bool attr_set[64] = {};   // per device: function attributes belong to the device's context
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ * 4096 * (int)sizeof(u64)));
+        attr_set[dev] = true;
+    }
     CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(kScanThreads), smem, s, p));
     return B2S_OK;
 }
@@ -288,6 +298,10 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
     if ((rc = idx->ws_counts.ensure((size_t)grid * chunk * sizeof(int))) != B2S_OK) return rc;
     if (seed && (rc = idx->ws_seed.ensure((size_t)chunk * sizeof(u64))) != B2S_OK) return rc;
 
+    // One scan launch covers the whole call and nothing is seeded: the last CTA of the scan does the
+    // merge (and, sharded with co-resident CTAs, the exchange) itself -- see scan_topk.cuh.
+    const bool fuse_tail = idx->opt_fused_tail && !seed && nq <= max_group && idx->done_counter != nullptr &&
+                           (idx->ex_call == nullptr || idx->ex_fused);
     for (int64_t c0 = 0; c0 < nq; c0 += chunk) {
         const int cn = (int)std::min<int64_t>(chunk, nq - c0);
         for (int pass = seed ? 0 : 1; pass < 2; ++pass) {
@@ -311,10 +325,31 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
                 // The scan only READS the corpus and the caller's queries unless a kernel of THIS call
                 // ran before it (query prep, seeding pass, an earlier group writing the same workspace).
                 p.pdl_late_wait = (late_wait_ok && !seed && nq <= max_group) ? 1 : 0;
+                p.fused_tail = 0;
+                if (fuse_tail) {
+                    p.fused_tail = idx->ex_call ? 2 : 1;
+                    p.done_counter = idx->done_counter;
+                    memset(&p.mp, 0, sizeof(p.mp));
+                    p.mp.lists = p.lists;
+                    p.mp.counts = p.counts;
+                    p.mp.num_lists = grid;
+                    p.mp.nq_lists = chunk;
+                    p.mp.lists_sorted = 1;
+                    p.mp.cap = cap;
+                    p.mp.k = k;
+                    p.mp.id_offset = idx->id_offset;
+                    p.mp.out_scores = out_scores;
+                    p.mp.out_ids = reinterpret_cast<long long*>(out_ids);
+                    if (idx->ex_call) p.ex = *idx->ex_call;
+                }
                 if ((rc = launch_scan(idx->dim, group, p, grid, s)) != B2S_OK) return rc;
                 idx->stats.kernel_launches++;
                 if (pass == 1) idx->stats.passes++;
                 g0 += group;
+            }
+            if (fuse_tail) {
+                if (idx->opt_timing) cudaEventRecord(idx->ev[2], s);
+                continue;   // merged (and exchanged) by the scan kernel's last CTA
             }
             MergeParams mp;
             memset(&mp, 0, sizeof(mp));
@@ -553,6 +588,11 @@ B2S_API int b2s_create(int dim, int metric, int device, b2s_index** out) {
         delete idx;
         return fail(B2S_ERR_CUDA, "cudaStreamCreate failed");
     }
+    if (cudaMalloc((void**)&idx->done_counter, sizeof(unsigned)) != cudaSuccess ||
+        cudaMemset(idx->done_counter, 0, sizeof(unsigned)) != cudaSuccess) {
+        cudaGetLastError();
+        idx->done_counter = nullptr;   // the fused tail is simply not used
+    }
     *out = idx;
     return B2S_OK;
 }
@@ -582,6 +622,7 @@ B2S_API int b2s_destroy(b2s_index* idx) {
     tensor_path_release(idx);
 #endif
     exchange_release(idx);
+    if (idx->done_counter) cudaFree(idx->done_counter);
     if (idx->pin_q) cudaFreeHost(idx->pin_q);
     if (idx->pin_out) cudaFreeHost(idx->pin_out);
     if (idx->ring) {
@@ -723,6 +764,8 @@ B2S_API int b2s_set_option(b2s_index* idx, const char* name, int64_t value) {
         idx->ev_valid = false;
     } else if (s == "tc_min_nq") {
         idx->opt_tc_min_nq = (int)std::max<int64_t>(1, value);
+    } else if (s == "fused_tail") {
+        idx->opt_fused_tail = value ? 1 : 0;
     } else if (s == "pdl") {
         if (value < 0 || value > 2) return fail(B2S_ERR_INVALID, "pdl must be 0, 1 or 2");
         idx->opt_pdl = (int)value;
@@ -755,6 +798,7 @@ B2S_API int64_t b2s_get_option(const b2s_index* idx, const char* name) {
     if (s == "timing") return idx->opt_timing;
     if (s == "tc_min_nq") return idx->opt_tc_min_nq;
     if (s == "pdl") return idx->opt_pdl;
+    if (s == "fused_tail") return idx->opt_fused_tail;
     if (s == "tc_sample_div") return idx->opt_tc_sample_div;
     if (s == "tc_shared_thr") return idx->opt_tc_shared_thr;
     if (s == "tc_chunk_tiles") return idx->opt_tc_chunk_lo == idx->opt_tc_chunk_hi ? idx->opt_tc_chunk_lo : 0;

@@ -53,6 +53,7 @@ __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
 
 // Store this rank's sorted top-k of global query gq (keys in buf[0..kk)) into every rank's slot and
 // publish the flag.  Block-wide.
+template <int NT = 512>
 __device__ __forceinline__ void exchange_push(const ExchangeArgs& ex, const MergeParams& p, const u64* buf, int kk,
                                               long long gq) {
     const int tid = threadIdx.x;
@@ -60,7 +61,7 @@ __device__ __forceinline__ void exchange_push(const ExchangeArgs& ex, const Merg
     const long long slot = ((long long)parity * ex.world + ex.rank) * ex.slot_stride;
     const long long ids_off = slot + (gq * p.k) * 8;
     const long long sc_off = slot + ex.nq * p.k * 8 + (gq * p.k) * 4;
-    for (int e = tid; e < p.k * ex.world; e += kMergeThreads) {
+    for (int e = tid; e < p.k * ex.world; e += NT) {
         const int peer = e / p.k, i = e - peer * p.k;
         float s = -FLT_MAX;
         long long id = -1;
@@ -83,6 +84,7 @@ __device__ __forceinline__ void exchange_push(const ExchangeArgs& ex, const Merg
 }
 
 // Wait for every rank's candidates of global query gq, merge world*k of them, write the final top-k.
+template <int NT = 512>
 __device__ __forceinline__ void exchange_wait_merge(const ExchangeArgs& ex, int k, u64* buf, long long gq) {
     const int tid = threadIdx.x;
     const int parity = (int)(ex.seq & 1u);
@@ -100,7 +102,7 @@ __device__ __forceinline__ void exchange_wait_merge(const ExchangeArgs& ex, int 
     }
     __syncthreads();
     const int total = ex.world * k;   // host guarantees total <= kMergeSortCap
-    for (int e = tid; e < total; e += kMergeThreads) {
+    for (int e = tid; e < total; e += NT) {
         const int r = e / k, i = e - r * k;
         const unsigned char* slot = ex.local_base + ((long long)parity * ex.world + r) * ex.slot_stride;
         const long long id = __ldcg(reinterpret_cast<const long long*>(slot + (gq * k + i) * 8));
@@ -109,8 +111,8 @@ __device__ __forceinline__ void exchange_wait_merge(const ExchangeArgs& ex, int 
         buf[e] = id < 0 ? 0ull : make_key(s, (uint32_t)e);
     }
     __syncthreads();
-    block_sort_desc(buf, total > 0 ? total : 1, tid);
-    for (int i = tid; i < k; i += kMergeThreads) {
+    block_sort_desc<NT>(buf, total > 0 ? total : 1, tid);
+    for (int i = tid; i < k; i += NT) {
         float s = -FLT_MAX;
         long long id = -1;
         if (i < total && buf[i] != 0ull) {

@@ -50,11 +50,12 @@ __device__ __forceinline__ int next_pow2(int v) {
 }
 
 // Block-wide: sort buf[0..m) descending (m <= kMergeSortCap), padding with 0 keys.
+template <int NT = 512>
 __device__ __forceinline__ void block_sort_desc(u64* buf, int m, int tid) {
     const int n = next_pow2(m);
-    for (int i = m + tid; i < n; i += kMergeThreads) buf[i] = 0ull;
+    for (int i = m + tid; i < n; i += NT) buf[i] = 0ull;
     __syncthreads();
-    bitonic_sort_desc(buf, n, tid, kMergeThreads, BlockSync());
+    bitonic_sort_desc(buf, n, tid, NT, BlockSync());
 }
 
 constexpr int kMergeMaxLists = 512;   // candidate lists per query (CTAs of the producing kernel)
@@ -72,7 +73,7 @@ __device__ __forceinline__ u64 fetch_candidate(const MergeParams& p, const int* 
         else hi = mid;
     }
     if (list_out) *list_out = lo;
-    return p.lists[((size_t)lo * p.nq_lists + q) * p.cap + (e - offs[lo])];
+    return __ldcg(p.lists + ((size_t)lo * p.nq_lists + q) * p.cap + (e - offs[lo]));
 }
 
 struct MergeSmem {
@@ -91,6 +92,7 @@ struct MergeSmem {
 
 // Block-wide: leave the best min(m, k..) candidate keys of query q sorted descending in sm.buf and
 // return how many of them are valid (>= min(k, total candidates)).
+template <int NT = 512>
 __device__ __forceinline__ int merge_lists_sorted(const MergeParams& p, const int q, MergeSmem& sm) {
     u64* buf = sm.buf;
     int* offs = sm.offs;
@@ -112,12 +114,12 @@ __device__ __forceinline__ int merge_lists_sorted(const MergeParams& p, const in
         // list can be cut at the first key under that floor: two dependent memory round trips in total,
         // no prefix sum, no gather of every candidate.
         u64* heads = reinterpret_cast<u64*>(hist);
-        for (int l = tid; l < kMergeMaxLists; l += kMergeThreads) {
+        for (int l = tid; l < kMergeMaxLists; l += NT) {
             int c = 0;
             u64 h = 0ull;
             if (l < L) {
-                c = p.counts[(size_t)l * p.nq_lists + q];
-                h = p.lists[((size_t)l * p.nq_lists + q) * p.cap];   // garbage when the list is empty
+                c = __ldcg(p.counts + (size_t)l * p.nq_lists + q);
+                h = __ldcg(p.lists + ((size_t)l * p.nq_lists + q) * p.cap);   // garbage when the list is empty
             }
             offs[l] = c;
             heads[l] = c > 0 ? h : 0ull;
@@ -130,12 +132,12 @@ __device__ __forceinline__ int merge_lists_sorted(const MergeParams& p, const in
         __syncthreads();
         {
             int mine = 0;
-            for (int l = tid; l < L; l += kMergeThreads) mine += heads[l] != 0ull;
+            for (int l = tid; l < L; l += NT) mine += heads[l] != 0ull;
             if (mine) atomicAdd(&s_nonempty, mine);
         }
         __syncthreads();
         if (s_nonempty >= p.k) {
-            for (int l = tid; l < L; l += kMergeThreads) {
+            for (int l = tid; l < L; l += NT) {
                 const u64 h = heads[l];
                 int rank = 0;
                 for (int j = 0; j < L; ++j) rank += heads[j] > h;
@@ -144,20 +146,20 @@ __device__ __forceinline__ int merge_lists_sorted(const MergeParams& p, const in
         }
         __syncthreads();
         const u64 floor_key = s_floor;
-        for (int l = tid; l < L; l += kMergeThreads) {
+        for (int l = tid; l < L; l += NT) {
             const int c = offs[l];
             const u64* lp = p.lists + ((size_t)l * p.nq_lists + q) * p.cap;
             u64 key = heads[l];
             for (int i = 0; i < c && key >= floor_key; ) {
                 const int pos = atomicAdd(&s_fill, 1);
                 if (pos < kMergeFastCap) sel[pos] = key;
-                if (++i < c) key = lp[i];
+                if (++i < c) key = __ldcg(lp + i);
             }
         }
         __syncthreads();
         const int C = s_fill;
         if (C <= kMergeFastCap) {
-            for (int t = tid; t < C; t += kMergeThreads) {
+            for (int t = tid; t < C; t += NT) {
                 const u64 key = sel[t];
                 int rank = 0;
                 for (int j = 0; j < C; ++j) rank += sel[j] > key;
@@ -170,23 +172,23 @@ __device__ __forceinline__ int merge_lists_sorted(const MergeParams& p, const in
     }
 
     // exclusive prefix sums of the per-list counts (Hillis-Steele in shared memory)
-    for (int l = tid; l < L; l += kMergeThreads) offs[l + 1] = p.counts[(size_t)l * p.nq_lists + q];
+    for (int l = tid; l < L; l += NT) offs[l + 1] = __ldcg(p.counts + (size_t)l * p.nq_lists + q);
     if (tid == 0) {
         offs[0] = 0;
         s_fill = 0;
     }
     __syncthreads();
     for (int d = 1; d < L; d <<= 1) {
-        int add[kMergeMaxLists / kMergeThreads];
+        int add[(kMergeMaxLists + NT - 1) / NT];
 #pragma unroll
-        for (int r = 0; r < kMergeMaxLists / kMergeThreads; ++r) {
-            const int l = tid + r * kMergeThreads + 1;
+        for (int r = 0; r < (kMergeMaxLists + NT - 1) / NT; ++r) {
+            const int l = tid + r * NT + 1;
             add[r] = (l <= L && l - d >= 1) ? offs[l - d] : 0;
         }
         __syncthreads();
 #pragma unroll
-        for (int r = 0; r < kMergeMaxLists / kMergeThreads; ++r) {
-            const int l = tid + r * kMergeThreads + 1;
+        for (int r = 0; r < (kMergeMaxLists + NT - 1) / NT; ++r) {
+            const int l = tid + r * NT + 1;
             if (l <= L) offs[l] += add[r];
         }
         __syncthreads();
@@ -201,13 +203,13 @@ __device__ __forceinline__ int merge_lists_sorted(const MergeParams& p, const in
     // in the answer -- typically ~2k of the M candidates.  They are compacted and rank-sorted
     // (each thread counts the keys greater than its own): no 4096-wide bitonic network.
     u64* heads = reinterpret_cast<u64*>(hist);   // [L] aliases the radix histogram (used later only)
-    for (int l = tid; l < L; l += kMergeThreads) heads[l] = 0ull;
+    for (int l = tid; l < L; l += NT) heads[l] = 0ull;
     if (tid == 0) {
         s_floor = 0ull;
         s_nonempty = 0;
     }
     __syncthreads();
-    for (int e = tid; e < M; e += kMergeThreads) {
+    for (int e = tid; e < M; e += NT) {
         int l;
         const u64 key = fetch_candidate(p, offs, L, q, e, &l);
         atomicMax(&heads[l], key);
@@ -216,12 +218,12 @@ __device__ __forceinline__ int merge_lists_sorted(const MergeParams& p, const in
     __syncthreads();
     {
         int mine = 0;
-        for (int l = tid; l < L; l += kMergeThreads) mine += heads[l] != 0ull;
+        for (int l = tid; l < L; l += NT) mine += heads[l] != 0ull;
         if (mine) atomicAdd(&s_nonempty, mine);
     }
     __syncthreads();
     if (s_nonempty >= p.k) {
-        for (int l = tid; l < L; l += kMergeThreads) {
+        for (int l = tid; l < L; l += NT) {
             const u64 h = heads[l];
             int rank = 0;
             for (int j = 0; j < L; ++j) rank += heads[j] > h;
@@ -230,7 +232,7 @@ __device__ __forceinline__ int merge_lists_sorted(const MergeParams& p, const in
     }
     __syncthreads();
     const u64 floor_key = s_floor;
-    for (int e = tid; e < M; e += kMergeThreads) {
+    for (int e = tid; e < M; e += NT) {
         const u64 key = (M <= kMergeSortCap) ? buf[e] : fetch_candidate(p, offs, L, q, e);
         if (key >= floor_key) {
             const int pos = atomicAdd(&s_fill, 1);
@@ -241,7 +243,7 @@ __device__ __forceinline__ int merge_lists_sorted(const MergeParams& p, const in
     const int C = s_fill;
     if (C <= kMergeFastCap) {
         __syncthreads();   // everyone has read s_fill / buf before buf is overwritten
-        for (int t = tid; t < C; t += kMergeThreads) {
+        for (int t = tid; t < C; t += NT) {
             const u64 key = sel[t];
             int rank = 0;
             for (int j = 0; j < C; ++j) rank += sel[j] > key;
@@ -275,9 +277,9 @@ __device__ __forceinline__ int merge_lists_sorted(const MergeParams& p, const in
                 const int nbits = (64 - bits_done) < kRadixBits ? (64 - bits_done) : kRadixBits;
                 const int shift = 64 - bits_done - nbits;
                 const u64 prefix = s_prefix;
-                for (int i = tid; i < kRadixBins; i += kMergeThreads) hist[i] = 0;
+                for (int i = tid; i < kRadixBins; i += NT) hist[i] = 0;
                 __syncthreads();
-                for (int e = tid; e < M; e += kMergeThreads) {
+                for (int e = tid; e < M; e += NT) {
                     const u64 key = in_smem ? buf[e] : fetch_candidate(p, offs, L, q, e);
                     const bool in_bucket = bits_done == 0 || (key >> (64 - bits_done)) == prefix;
                     if (in_bucket) atomicAdd(&hist[(int)((key >> shift) & ((1u << nbits) - 1u))], 1);
@@ -313,7 +315,7 @@ __device__ __forceinline__ int merge_lists_sorted(const MergeParams& p, const in
             // gather winners (prefix bits above the bucket) and the bucket itself
             const int bits_done = s_bits_done;
             const u64 prefix = s_prefix;
-            for (int e = tid; e < M; e += kMergeThreads) {
+            for (int e = tid; e < M; e += NT) {
                 const u64 key = fetch_candidate(p, offs, L, q, e);
                 const bool take = bits_done == 0 || (key >> (64 - bits_done)) >= prefix;
                 if (take) {
@@ -326,7 +328,7 @@ __device__ __forceinline__ int merge_lists_sorted(const MergeParams& p, const in
         }
     }
 
-    if (!sorted_done) block_sort_desc(buf, m_sorted > 0 ? m_sorted : 1, tid);
+    if (!sorted_done) block_sort_desc<NT>(buf, m_sorted > 0 ? m_sorted : 1, tid);
     return m_sorted;
 }
 

@@ -15,6 +15,8 @@
 // are appended to the shared-memory candidate list (select.cuh); everything else is dropped in
 // registers, so the [N] score vector never exists in memory.
 #pragma once
+#include "exchange.cuh"
+#include "merge_topk.cuh"
 #include "select.cuh"
 
 namespace b2s {
@@ -39,6 +41,13 @@ struct ScanParams {
     int pdl_late_wait;     // 1: nothing this kernel READS is produced by the preceding kernel of the
                            // stream, so the PDL wait is deferred to just before the list write-out
                            // (the scan of query i+1 then overlaps the merge of query i)
+    // Fused tail: the LAST CTA to publish its lists (ticket from *done_counter) merges all lists of
+    // the launch's queries itself -- no separate merge kernel, no kernel boundary.  1 = write the
+    // final top-k (mp.out_*); 2 = sharded search: push to the peers, wait, merge (ex).
+    int fused_tail;
+    unsigned* done_counter;   // zero before the launch; the last CTA resets it
+    MergeParams mp;
+    ExchangeArgs ex;
 };
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
@@ -214,6 +223,45 @@ scan_topk_kernel(const ScanParams p) {
         u64* dst = p.lists + ((size_t)blockIdx.x * p.nq_lists + (p.q_begin + q)) * p.cap;
         for (int i = tid; i < c; i += kScanThreads) dst[i] = entries[(size_t)q * p.cap + i];
         if (tid == 0) p.counts[(size_t)blockIdx.x * p.nq_lists + (p.q_begin + q)] = c;
+    }
+    if (p.fused_tail == 0) return;
+
+    // ---- fused tail: last CTA done merges (threadfence reduction pattern) ------------------------
+    __shared__ MergeSmem sm;
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned ticket = atomicAdd(p.done_counter, 1u);
+        s_last = ticket == gridDim.x - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid == 0) *p.done_counter = 0u;   // ready for the next launch (stream-ordered after this kernel)
+    for (int q = 0; q < p.nq_valid; ++q) {
+        const int lq = p.q_begin + q;     // list / output index of this query inside the call
+        const int m_sorted = merge_lists_sorted<kScanThreads>(p.mp, lq, sm);
+        const int kk = m_sorted < p.mp.k ? m_sorted : p.mp.k;
+        if (p.fused_tail == 1) {
+            for (int i = tid; i < p.mp.k; i += kScanThreads) {
+                float s = -FLT_MAX;
+                long long id = -1;
+                if (i < kk) {
+                    const u64 key = sm.buf[i];
+                    s = key_score(key);
+                    id = (long long)key_row(key) + p.mp.id_offset;
+                }
+                p.mp.out_scores[(size_t)lq * p.mp.k + i] = s;
+                p.mp.out_ids[(size_t)lq * p.mp.k + i] = id;
+            }
+        } else {
+            const long long gq = (long long)p.ex.q_offset + lq;
+            exchange_push<kScanThreads>(p.ex, p.mp, sm.buf, kk, gq);
+            __syncthreads();
+            exchange_wait_merge<kScanThreads>(p.ex, p.mp.k, sm.buf, gq);
+        }
+        __syncthreads();
     }
 }
 
