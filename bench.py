@@ -420,7 +420,8 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": workload_config(n_gpus),
-                "roofline": {"bound": "hbm", "kernel": "scan_topk_kernel (K1)", "achieved": achieved, "peak": peak,
+                "roofline": {"bound": "hbm", "kernel": "scan_topk_kernel (K1; its last CTA also merges the candidate lists"
+                                                       + (" and exchanges them with the peers)" if n_gpus > 1 else ")"), "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": local_bytes,
                              "kernel_ms_avg": k1_ms,
