@@ -98,7 +98,8 @@ B2S_API int b2s_set_id_offset(b2s_index* idx, int64_t offset);
  *   "scan_ctas_per_sm"  CTAs per SM of the scan kernel (default 2)
  *   "keep_f32"    1: keep an fp32 copy of added rows for exact re-scoring
  *   "rescore_pad" extra candidates re-scored in fp32 when keep_f32 is on
- *   "timing"      1: record CUDA-event timings into b2s_stats (adds syncs)
+ *   "timing"      N > 0: every N-th search records CUDA events around its dominant kernel and the
+ *                 whole call (b2s_last_stats / b2s_read_timings); 0 = off
  *   "pdl"         0 off | 1 (default) programmatic dependent launch hides the launch latency
  *                 between the scan and merge kernels | 2 additionally lets the scan of call i+1
  *                 overlap the merge of call i; valid only if the query buffer of a call is not

@@ -103,7 +103,9 @@ struct b2s_index {
     int opt_scan_ctas_per_sm = 2;
     int opt_keep_f32 = 0;
     int opt_rescore_pad = 32;
-    int opt_timing = 0;
+    int opt_timing = 0;           // N > 0: every N-th search call records CUDA events
+    bool time_this = false;       // the current call is one of them
+    int64_t timing_seq = 0;
     int opt_tc_min_nq = 3;
     int opt_pdl = 1;              // 1: programmatic dependent launch hides launch latencies (always safe);
                                   // 2: also overlap the scan of call i+1 with the merge of call i -- only
@@ -348,7 +350,7 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
                 g0 += group;
             }
             if (fuse_tail) {
-                if (idx->opt_timing) cudaEventRecord(idx->ev[2], s);
+                if (idx->time_this) cudaEventRecord(idx->ev[2], s);
                 continue;   // merged (and exchanged) by the scan kernel's last CTA
             }
             MergeParams mp;
@@ -367,7 +369,7 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
                 mp.out_scores = out_scores + (size_t)c0 * k;
                 mp.out_ids = reinterpret_cast<long long*>(out_ids) + (size_t)c0 * k;
             }
-            if (pass == 1 && idx->opt_timing && c0 == 0) cudaEventRecord(idx->ev[2], s);
+            if (pass == 1 && idx->time_this && c0 == 0) cudaEventRecord(idx->ev[2], s);
             if ((rc = launch_merge(idx, mp, cn, (int)c0, s)) != B2S_OK) return rc;
             idx->stats.kernel_launches++;
         }
@@ -395,13 +397,15 @@ int search_core(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, in
 
     memset(&idx->stats, 0, sizeof(idx->stats));
     idx->stats.corpus_bytes = idx->n * (int64_t)idx->dim * 2;
-    if (idx->opt_timing && idx->ring) {
+    // "timing" = N: every N-th search records its events (events between kernels switch programmatic
+    // dependent launch off for that call, so sampling keeps the steady state undisturbed)
+    idx->time_this = idx->opt_timing > 0 && idx->ring && (idx->timing_seq++ % idx->opt_timing) == 0;
+    if (idx->time_this) {
         idx->ev = idx->ring + 4 * (idx->ring_calls % kTimingSlots);
         idx->ring_calls++;
         cudaEventRecord(idx->ev[0], s);
         idx->ev_valid = true;
     } else {
-        idx->opt_timing = 0;
         idx->ev_valid = false;
     }
 
@@ -416,7 +420,7 @@ int search_core(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, in
         mp.out_ids = reinterpret_cast<long long*>(out_ids);
         if ((rc = launch_merge(idx, mp, (int)nq, 0, s)) != B2S_OK) return rc;
         idx->stats.kernel_launches++;
-        if (idx->opt_timing) {
+        if (idx->time_this) {
             cudaEventRecord(idx->ev[1], s);
             cudaEventRecord(idx->ev[2], s);
             cudaEventRecord(idx->ev[3], s);
@@ -428,7 +432,7 @@ int search_core(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, in
         fill_empty_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(out_scores, reinterpret_cast<long long*>(out_ids), cnt);
         CUDA_TRY(cudaGetLastError());
         idx->stats.kernel_launches++;
-        if (idx->opt_timing) {
+        if (idx->time_this) {
             cudaEventRecord(idx->ev[1], s);
             cudaEventRecord(idx->ev[2], s);
             cudaEventRecord(idx->ev[3], s);
@@ -465,7 +469,7 @@ int search_core(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, in
             idx->stats.kernel_launches++;
             qf = reinterpret_cast<const float*>(idx->ws_qf32.p);
         }
-        if (idx->opt_timing) cudaEventRecord(idx->ev[1], s);
+        if (idx->time_this) cudaEventRecord(idx->ev[1], s);
         // late PDL wait only if no kernel of this call precedes the scan and no event sits between
         // consecutive calls' kernels (timing on) -- see scan_topk.cuh
         const bool late_wait_ok = (qf == reinterpret_cast<const float*>(queries)) && idx->opt_pdl == 2;
@@ -477,7 +481,7 @@ int search_core(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, in
         if (rc != B2S_OK) return rc;
 #endif
     }
-    if (idx->opt_timing) cudaEventRecord(idx->ev[3], s);
+    if (idx->time_this) cudaEventRecord(idx->ev[3], s);
     return B2S_OK;
 }
 
@@ -500,7 +504,7 @@ int search_impl(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, in
         reinterpret_cast<const long long*>(ci), k2, idx->id_offset, k, out_scores, reinterpret_cast<long long*>(out_ids));
     CUDA_TRY(cudaGetLastError());
     idx->stats.kernel_launches++;
-    if (idx->opt_timing && idx->ev_valid) cudaEventRecord(idx->ev[3], s);
+    if (idx->time_this && idx->ev_valid) cudaEventRecord(idx->ev[3], s);
     return B2S_OK;
 }
 
@@ -759,7 +763,8 @@ B2S_API int b2s_set_option(b2s_index* idx, const char* name, int64_t value) {
             if (!idx->ring) return fail(B2S_ERR_NOMEM, "host allocation failed");
             for (int i = 0; i < 4 * kTimingSlots; ++i) CUDA_TRY(cudaEventCreate(&idx->ring[i]));
         }
-        idx->opt_timing = value ? 1 : 0;
+        idx->opt_timing = (int)std::min<int64_t>(1 << 20, std::max<int64_t>(0, value));
+        idx->timing_seq = 0;
         idx->ring_calls = 0;
         idx->ev_valid = false;
     } else if (s == "tc_min_nq") {

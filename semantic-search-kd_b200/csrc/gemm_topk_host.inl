@@ -214,12 +214,12 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
         p.chunk_tiles = qblocks > 1 ? tc_pick_chunk(tiles_all, qblocks, pairs, idx->opt_tc_chunk_lo, idx->opt_tc_chunk_hi)
                                     : tc_pick_chunk(tiles_all, 1, pairs, 8, 32);
         p.num_chunks = (tiles_all + p.chunk_tiles - 1) / p.chunk_tiles;
-        if (idx->opt_timing && c0 == 0) cudaEventRecord(idx->ev[1], s);
+        if (idx->time_this && c0 == 0) cudaEventRecord(idx->ev[1], s);
         if (pair_mode) CUDA_TRY((tc_launch<false, true>(ctas, L.total + 1024, s, corpus_map, qmap, p)));
         else CUDA_TRY((tc_launch<false, false>(ctas, L.total + 1024, s, corpus_map, qmap, p)));
         idx->stats.kernel_launches++;
         idx->stats.passes += qblocks;
-        if (idx->opt_timing && c0 == 0) cudaEventRecord(idx->ev[2], s);
+        if (idx->time_this && c0 == 0) cudaEventRecord(idx->ev[2], s);
 
         MergeParams mp;
         memset(&mp, 0, sizeof(mp));
