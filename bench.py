@@ -177,6 +177,7 @@ def gpu_cfg0_report(torch, pkg, dev, kinds=("isotropic", "clustered")):
         torch.cuda.synchronize()
         tb = time.perf_counter() - t0
         idx.search(Q[:8], K)
+        idx.search(Q, K)                              # warm: workspaces, tensor maps
         t0 = time.perf_counter()
         D, I = idx.search(Q, K)                       # one batched call (tensor path)
         t_batch = time.perf_counter() - t0

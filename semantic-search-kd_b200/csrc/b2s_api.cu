@@ -118,7 +118,7 @@ struct b2s_index {
     int opt_tc_chunk_lo = 48;     // tiles per work item when several query blocks share the corpus
     int opt_tc_chunk_hi = 96;
     // workspace
-    DevBuf ws_lists, ws_counts, ws_thr, ws_gmax, ws_hist, ws_hcfg, ws_rs_scores, ws_rs_ids, ws_seed, ws_qf32, ws_qbf16, ws_io_q, ws_io_scores, ws_io_ids, ws_tmp;
+    DevBuf ws_lists, ws_counts, ws_thr, ws_gmax, ws_hist, ws_hcfg, ws_rs_scores, ws_rs_ids, ws_seed, ws_qf32, ws_qbf16, ws_io_q, ws_io_ids, ws_tmp;
     void* pin_q = nullptr;
     void* pin_out = nullptr;
     size_t pin_q_bytes = 0, pin_out_bytes = 0;
@@ -619,7 +619,6 @@ B2S_API int b2s_destroy(b2s_index* idx) {
     idx->ws_qf32.release();
     idx->ws_qbf16.release();
     idx->ws_io_q.release();
-    idx->ws_io_scores.release();
     idx->ws_io_ids.release();
     idx->ws_tmp.release();
 #ifndef B2S_NO_TENSOR_PATH
@@ -831,8 +830,8 @@ B2S_API int b2s_search(b2s_index* idx, const float* queries, int64_t nq, int k, 
     const size_t sbytes = (size_t)nq * k * sizeof(float);
     const size_t ibytes = (size_t)nq * k * sizeof(int64_t);
     if ((rc = idx->ws_io_q.ensure(qbytes)) != B2S_OK) return rc;
-    if ((rc = idx->ws_io_scores.ensure(sbytes)) != B2S_OK) return rc;
-    if ((rc = idx->ws_io_ids.ensure(ibytes)) != B2S_OK) return rc;
+    if ((rc = idx->ws_io_ids.ensure(ibytes + sbytes)) != B2S_OK) return rc;   // [ids | scores]: one D2H copy
+    float* io_scores = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(idx->ws_io_ids.p) + ibytes);
     const bool small = qbytes <= ((size_t)1 << 20) && (sbytes + ibytes) <= ((size_t)1 << 20);
     if (small) {
         // stage through pinned memory so that both copies are truly asynchronous DMA
@@ -843,19 +842,18 @@ B2S_API int b2s_search(b2s_index* idx, const float* queries, int64_t nq, int k, 
     } else {
         CUDA_TRY(cudaMemcpyAsync(idx->ws_io_q.p, queries, qbytes, cudaMemcpyHostToDevice, idx->stream));
     }
-    rc = search_impl(idx, idx->ws_io_q.p, B2S_DTYPE_F32, nq, k, reinterpret_cast<float*>(idx->ws_io_scores.p),
+    rc = search_impl(idx, idx->ws_io_q.p, B2S_DTYPE_F32, nq, k, io_scores,
                      reinterpret_cast<int64_t*>(idx->ws_io_ids.p), idx->stream);
     if (rc != B2S_OK) return rc;
     if (small) {
         unsigned char* po = reinterpret_cast<unsigned char*>(idx->pin_out);
-        CUDA_TRY(cudaMemcpyAsync(po, idx->ws_io_ids.p, ibytes, cudaMemcpyDeviceToHost, idx->stream));
-        CUDA_TRY(cudaMemcpyAsync(po + ibytes, idx->ws_io_scores.p, sbytes, cudaMemcpyDeviceToHost, idx->stream));
+        CUDA_TRY(cudaMemcpyAsync(po, idx->ws_io_ids.p, ibytes + sbytes, cudaMemcpyDeviceToHost, idx->stream));
         CUDA_TRY(cudaStreamSynchronize(idx->stream));
         memcpy(out_ids, po, ibytes);
         memcpy(out_scores, po + ibytes, sbytes);
     } else {
         CUDA_TRY(cudaMemcpyAsync(out_ids, idx->ws_io_ids.p, ibytes, cudaMemcpyDeviceToHost, idx->stream));
-        CUDA_TRY(cudaMemcpyAsync(out_scores, idx->ws_io_scores.p, sbytes, cudaMemcpyDeviceToHost, idx->stream));
+        CUDA_TRY(cudaMemcpyAsync(out_scores, io_scores, sbytes, cudaMemcpyDeviceToHost, idx->stream));
         CUDA_TRY(cudaStreamSynchronize(idx->stream));
     }
     return B2S_OK;
@@ -1181,18 +1179,17 @@ B2S_API int b2s_search_sharded(b2s_index* idx, const float* queries, int64_t nq,
     const size_t sbytes = (size_t)nq * k * sizeof(float);
     const size_t ibytes = (size_t)nq * k * sizeof(int64_t);
     if ((rc = idx->ws_io_q.ensure(qbytes)) != B2S_OK) return rc;
-    if ((rc = idx->ws_io_scores.ensure(sbytes)) != B2S_OK) return rc;
-    if ((rc = idx->ws_io_ids.ensure(ibytes)) != B2S_OK) return rc;
+    if ((rc = idx->ws_io_ids.ensure(ibytes + sbytes)) != B2S_OK) return rc;   // [ids | scores]: one D2H copy
+    float* io_scores = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(idx->ws_io_ids.p) + ibytes);
     if ((rc = ensure_pinned(&idx->pin_q, &idx->pin_q_bytes, qbytes)) != B2S_OK) return rc;
     if ((rc = ensure_pinned(&idx->pin_out, &idx->pin_out_bytes, sbytes + ibytes)) != B2S_OK) return rc;
     memcpy(idx->pin_q, queries, qbytes);
     CUDA_TRY(cudaMemcpyAsync(idx->ws_io_q.p, idx->pin_q, qbytes, cudaMemcpyHostToDevice, idx->stream));
-    rc = search_sharded_impl(idx, idx->ws_io_q.p, B2S_DTYPE_F32, nq, k, reinterpret_cast<float*>(idx->ws_io_scores.p),
+    rc = search_sharded_impl(idx, idx->ws_io_q.p, B2S_DTYPE_F32, nq, k, io_scores,
                              reinterpret_cast<int64_t*>(idx->ws_io_ids.p), idx->stream, 0);
     if (rc != B2S_OK) return rc;
     unsigned char* po = reinterpret_cast<unsigned char*>(idx->pin_out);
-    CUDA_TRY(cudaMemcpyAsync(po, idx->ws_io_ids.p, ibytes, cudaMemcpyDeviceToHost, idx->stream));
-    CUDA_TRY(cudaMemcpyAsync(po + ibytes, idx->ws_io_scores.p, sbytes, cudaMemcpyDeviceToHost, idx->stream));
+    CUDA_TRY(cudaMemcpyAsync(po, idx->ws_io_ids.p, ibytes + sbytes, cudaMemcpyDeviceToHost, idx->stream));
     CUDA_TRY(cudaStreamSynchronize(idx->stream));
     memcpy(out_ids, po, ibytes);
     memcpy(out_scores, po + ibytes, sbytes);

@@ -73,10 +73,9 @@ class ShardedFlatIPIndex:
             raise IndexBuildError("exchange must be 'auto', 'peer' or 'nccl'")
         # the fused peer-memory exchange needs real GPUs and the CUDA merge (not the injected test doubles)
         if exchange == "auto":
-            exchange = "peer" if (merge_fn is None and local_index is None or
-                                  (merge_fn is None and isinstance(local_index, FlatIPIndex))) and \
-                                 torch is not None and torch.cuda.is_available() and \
-                                 dist.get_backend(group) == "nccl" else "nccl"
+            real_gpu_path = (merge_fn is None and (local_index is None or isinstance(local_index, FlatIPIndex)) and
+                             torch is not None and torch.cuda.is_available() and dist.get_backend(group) == "nccl")
+            exchange = "peer" if real_gpu_path else "nccl"
         self.exchange = exchange
         self._ex_slot_bytes = int(exchange_slot_bytes)
         self._ex_max_nq = int(exchange_max_nq)
