@@ -462,6 +462,12 @@ def run_ours(args):
                 line["cfg0_recall"] = gpu_cfg0_report(torch, pkg, dev)
             except Exception as e:
                 line["cfg0_recall"] = {"error": str(e)}
+            try:
+                # the reference's HNSW configuration on the same host cores, same run (clustered cfg0 data: the
+                # isotropic set takes minutes to build and is timed by `--impl reference` at N = 1)
+                line["cpu_hnsw"] = cpu_hnsw_report("clustered")
+            except Exception as e:
+                line["cpu_hnsw"] = {"error": str(e)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

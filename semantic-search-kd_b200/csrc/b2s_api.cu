@@ -291,7 +291,6 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
     const int64_t units = (idx->n + unit - 1) / unit;
     if ((int64_t)grid > units) grid = (int)units;
     grid = std::min(grid, kMergeMaxLists);
-    const int64_t rows_per_cta = ((units + grid - 1) / grid) * unit;
     const int max_group = scan_max_nq(idx->dim);
 
     const int chunk = (int)std::min<int64_t>(nq, kScanQueryChunk);
@@ -314,7 +313,6 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
                 p.corpus = reinterpret_cast<const uint4*>(idx->rows);
                 p.queries = q_f32 + (size_t)c0 * idx->dim;
                 p.n_rows = idx->n;
-                p.rows_per_cta = rows_per_cta;
                 p.q_begin = g0;
                 p.nq_valid = group;
                 p.k = k;

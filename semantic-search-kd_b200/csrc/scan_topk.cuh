@@ -28,7 +28,6 @@ struct ScanParams {
     const uint4* corpus;   // bf16 rows, row-major, dim*2 bytes each (16-byte aligned)
     const float* queries;  // fp32 [nq_total, dim]; this launch uses rows q_begin .. q_begin+NQ-1
     long long n_rows;      // rows in the shard
-    long long rows_per_cta;  // unused by the grid-stride schedule (kept for diagnostics)
     int q_begin;
     int nq_valid;          // how many of the NQ register queries are real (others masked)
     int k;
