@@ -135,7 +135,7 @@ struct b2s_index {
         unsigned char* local = nullptr;
         size_t bytes = 0;
         int world = 0, rank = 0, max_nq = 0;
-        long long slot_stride = 0, flags_off = 0;
+        long long slot_stride = 0, flags_off = 0, ll_off = 0, ll_entries = 0;
         unsigned char** peers_dev = nullptr;   // device array [world]
         std::vector<void*> opened;             // cudaIpcOpenMemHandle'd peer mappings
         unsigned* status = nullptr;            // device word
@@ -146,6 +146,7 @@ struct b2s_index {
     int ex_fused = 0;
     unsigned* done_counter = nullptr;   // device word for the scan kernel's fused merge tail
     int opt_fused_tail = 1;
+    int opt_exchange_ll = 1;            // fused exchange: tagged 8-byte words instead of payload + fence + flag
 #ifndef B2S_NO_TENSOR_PATH
     TensorPathState tc;
 #endif
@@ -766,6 +767,8 @@ B2S_API int b2s_set_option(b2s_index* idx, const char* name, int64_t value) {
         idx->ev_valid = false;
     } else if (s == "tc_min_nq") {
         idx->opt_tc_min_nq = (int)std::max<int64_t>(1, value);
+    } else if (s == "exchange_ll") {
+        idx->opt_exchange_ll = value ? 1 : 0;
     } else if (s == "fused_tail") {
         idx->opt_fused_tail = value ? 1 : 0;
     } else if (s == "pdl") {
@@ -1056,7 +1059,9 @@ B2S_API int b2s_exchange_create(b2s_index* idx, int world, int rank, int64_t slo
     ex.max_nq = max_nq;
     ex.slot_stride = (slot_bytes + 255) / 256 * 256;
     ex.flags_off = 2ll * world * ex.slot_stride;
-    ex.bytes = (size_t)ex.flags_off + (size_t)2 * world * max_nq * sizeof(unsigned);
+    ex.ll_off = ((ex.flags_off + (long long)2 * world * max_nq * (long long)sizeof(unsigned)) + 255) / 256 * 256;
+    ex.ll_entries = std::min<long long>(ex.slot_stride / 12, 131072);   // fused calls are small: <= #SMs queries
+    ex.bytes = (size_t)ex.ll_off + (size_t)2 * world * (size_t)ex.ll_entries * 24;
     CUDA_TRY(cudaMalloc((void**)&ex.local, ex.bytes));
     CUDA_TRY(cudaMemset(ex.local, 0, ex.bytes));
     CUDA_TRY(cudaMalloc((void**)&ex.status, sizeof(unsigned)));
@@ -1140,6 +1145,9 @@ static int search_sharded_impl(b2s_index* idx, const void* queries, int q_dtype,
         a.seq = ++ex.seq;
         // one kernel when every CTA of the merge is co-resident on every rank, else push / wait split
         idx->ex_fused = (phase == 0 && nq <= idx->num_sms) ? 1 : 0;
+        a.use_ll = (idx->ex_fused && idx->opt_exchange_ll && nq * (int64_t)k <= ex.ll_entries) ? 1 : 0;
+        a.ll_off = ex.ll_off;
+        a.ll_entries = ex.ll_entries;
         idx->ex_call = &a;
         rc = search_impl(idx, queries, q_dtype, nq, k, out_scores, out_ids, s);
         idx->ex_call = nullptr;

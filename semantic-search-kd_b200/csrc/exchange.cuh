@@ -40,6 +40,12 @@ struct ExchangeArgs {
     unsigned* status;                  // device word, 0 = ok
     float* out_scores;                 // [nq, k] final
     long long* out_ids;
+    // low-latency protocol (fused mode): candidates travel as three 8-byte words, each tagged with the
+    // call's sequence number in its high half -- data IS the flag, so there is no fence and no second
+    // message: one NVLink one-way trip instead of write + system fence + flag.
+    int use_ll;
+    long long ll_off;                  // byte offset of the LL region: [2 parities][world][ll_entries][3] u64
+    long long ll_entries;              // candidates per (parity, source rank)
 };
 
 __device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
@@ -127,6 +133,97 @@ __device__ __forceinline__ void exchange_wait_merge(const ExchangeArgs& ex, int 
     }
 }
 
+__device__ __forceinline__ void st_relaxed_sys_u64(u64* p, u64 v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u64 ld_relaxed_sys_u64(const u64* p) {
+    u64 v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// LL push: entry = {seq|score bits, seq|id low, seq|id high}; 8-byte stores are single-copy atomic, so a
+// reader that sees the tag sees the payload of that word.
+template <int NT = 512>
+__device__ __forceinline__ void exchange_push_ll(const ExchangeArgs& ex, const MergeParams& p, const u64* buf, int kk,
+                                                 long long gq) {
+    const int tid = threadIdx.x;
+    const int parity = (int)(ex.seq & 1u);
+    const long long entry0 = ((long long)parity * ex.world + ex.rank) * ex.ll_entries + gq * p.k;
+    const u64 tag = (u64)ex.seq << 32;
+    for (int e = tid; e < p.k * ex.world; e += NT) {
+        const int peer = e / p.k, i = e - peer * p.k;
+        float s = -FLT_MAX;
+        long long id = -1;
+        if (i < kk) {
+            const u64 key = buf[i];
+            s = key_score(key);
+            id = (long long)key_row(key) + p.id_offset;
+        }
+        u64* dst = reinterpret_cast<u64*>(ex.peer_base[peer] + ex.ll_off) + (entry0 + i) * 3;
+        st_relaxed_sys_u64(dst, tag | (u64)__float_as_uint(s));
+        st_relaxed_sys_u64(dst + 1, tag | (u64)(uint32_t)id);
+        st_relaxed_sys_u64(dst + 2, tag | (u64)(uint32_t)((unsigned long long)id >> 32));
+    }
+}
+
+// LL wait + merge: every thread polls its own candidate's three words in local memory.
+template <int NT = 512>
+__device__ __forceinline__ void exchange_wait_merge_ll(const ExchangeArgs& ex, int k, u64* buf, long long gq) {
+    const int tid = threadIdx.x;
+    const int parity = (int)(ex.seq & 1u);
+    const int total = ex.world * k;   // host guarantees total <= kMergeSortCap
+    const u64* ll = reinterpret_cast<const u64*>(ex.local_base + ex.ll_off);
+    for (int e = tid; e < total; e += NT) {
+        const int r = e / k, i = e - r * k;
+        const u64* src = ll + (((long long)parity * ex.world + r) * ex.ll_entries + gq * k + i) * 3;
+        u64 w0, w1, w2;
+        const long long t0 = clock64();
+        while (true) {
+            w0 = ld_relaxed_sys_u64(src);
+            w1 = ld_relaxed_sys_u64(src + 1);
+            w2 = ld_relaxed_sys_u64(src + 2);
+            if ((uint32_t)(w0 >> 32) == ex.seq && (uint32_t)(w1 >> 32) == ex.seq && (uint32_t)(w2 >> 32) == ex.seq) break;
+            if (clock64() - t0 > ex.timeout_cycles) {
+                atomicExch(ex.status, ex.seq);
+                w1 = w2 = 0xffffffffull;   // id -1: ignored
+                break;
+            }
+        }
+        const long long id = (long long)(((u64)(uint32_t)w2 << 32) | (u64)(uint32_t)w1);
+        buf[e] = id < 0 ? 0ull : make_key(__uint_as_float((uint32_t)w0), (uint32_t)e);
+    }
+    __syncthreads();
+    block_sort_desc<NT>(buf, total > 0 ? total : 1, tid);
+    for (int i = tid; i < k; i += NT) {
+        float s = -FLT_MAX;
+        long long id = -1;
+        if (i < total && buf[i] != 0ull) {
+            const int pos = (int)key_row(buf[i]);
+            const int r = pos / k, j = pos - r * k;
+            const u64* src = ll + (((long long)parity * ex.world + r) * ex.ll_entries + gq * k + j) * 3;
+            s = __uint_as_float((uint32_t)__ldcg(src));
+            id = (long long)(((u64)(uint32_t)__ldcg(src + 2) << 32) | (u64)(uint32_t)__ldcg(src + 1));
+        }
+        ex.out_scores[gq * k + i] = s;
+        ex.out_ids[gq * k + i] = id;
+    }
+}
+
+// push + wait + merge of one query inside a block that holds its sorted local top-k in buf
+template <int NT = 512>
+__device__ __forceinline__ void exchange_fused(const ExchangeArgs& ex, const MergeParams& p, u64* buf, int kk, long long gq) {
+    if (ex.use_ll) {
+        exchange_push_ll<NT>(ex, p, buf, kk, gq);
+        __syncthreads();
+        exchange_wait_merge_ll<NT>(ex, p.k, buf, gq);
+    } else {
+        exchange_push<NT>(ex, p, buf, kk, gq);
+        __syncthreads();
+        exchange_wait_merge<NT>(ex, p.k, buf, gq);
+    }
+}
+
 template <bool FUSED>
 __global__ void __launch_bounds__(kMergeThreads) merge_exchange_kernel(const MergeParams p, const ExchangeArgs ex) {
     __shared__ MergeSmem sm;
@@ -136,11 +233,8 @@ __global__ void __launch_bounds__(kMergeThreads) merge_exchange_kernel(const Mer
     grid_dep_wait();
     const int m_sorted = merge_lists_sorted(p, q, sm);
     const int kk = m_sorted < p.k ? m_sorted : p.k;
-    exchange_push(ex, p, sm.buf, kk, gq);
-    if (FUSED) {
-        __syncthreads();
-        exchange_wait_merge(ex, p.k, sm.buf, gq);
-    }
+    if (FUSED) exchange_fused(ex, p, sm.buf, kk, gq);
+    else exchange_push(ex, p, sm.buf, kk, gq);
 }
 
 __global__ void __launch_bounds__(kMergeThreads) exchange_wait_merge_kernel(const ExchangeArgs ex, int k) {

@@ -256,9 +256,7 @@ scan_topk_kernel(const ScanParams p) {
             }
         } else {
             const long long gq = (long long)p.ex.q_offset + lq;
-            exchange_push<kScanThreads>(p.ex, p.mp, sm.buf, kk, gq);
-            __syncthreads();
-            exchange_wait_merge<kScanThreads>(p.ex, p.mp.k, sm.buf, gq);
+            exchange_fused<kScanThreads>(p.ex, p.mp, sm.buf, kk, gq);
         }
         __syncthreads();
     }
