@@ -105,6 +105,15 @@ class Clocks:
 # --------------------------------------------------------------------------------------------
 # CPU legs (oracle port) -- the only place bench.py touches oracle/
 # --------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    """Threads the CPU legs use: every core this process may run on (torchrun exports OMP_NUM_THREADS=1 to
+    its workers, which would silently turn the reference arm into a single-core run)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_flat_qps(n_queries: int, warmup: int = 1):
     """Batch-1 exact flat search on the host cores over a 1/8 row sample; returns (qps_full, info)."""
     from oracle import oracle as orc
@@ -112,14 +121,15 @@ def cpu_flat_qps(n_queries: int, warmup: int = 1):
     rows = N_ROWS // CPU_SAMPLE_DIV
     X = orc.gen_unit_rows(rows, DIM, 0)
     Q = orc.gen_unit_rows(max(n_queries, 1) + warmup, DIM, 1)
+    nt = host_threads()
     for i in range(warmup):
-        orc.flat_ip_topk(X, Q[i:i + 1], K, acc="f32")
+        orc.flat_ip_topk(X, Q[i:i + 1], K, acc="f32", nthreads=nt)
     t0 = time.perf_counter()
     for i in range(n_queries):
-        orc.flat_ip_topk(X, Q[warmup + i:warmup + i + 1], K, acc="f32")
+        orc.flat_ip_topk(X, Q[warmup + i:warmup + i + 1], K, acc="f32", nthreads=nt)
     dt = time.perf_counter() - t0
     per_query_full = dt / max(1, n_queries) * CPU_SAMPLE_DIV
-    info = {"cores": orc.num_threads(), "kind": "port",
+    info = {"cores": nt, "kind": "port",
             "sample": f"{n_queries} batch-1 queries, fp32 flat scan (oracle/flat_ip.c, OpenMP) over "
                       f"{rows} of {N_ROWS} rows (1/{CPU_SAMPLE_DIV} sample); per-query time x{CPU_SAMPLE_DIV}",
             "ms_per_query_full_corpus": per_query_full * 1e3}
@@ -150,17 +160,18 @@ def cpu_hnsw_report(kind="isotropic", n=100_000, nq=1000):
     from oracle import oracle as orc
     X, Q = cfg0_data(kind, n, nq)
     t0 = time.perf_counter()
-    h = orc.HnswRef(X, 32, 200)
+    nt = host_threads()
+    h = orc.HnswRef(X, 32, 200, nthreads=nt)
     tb = time.perf_counter() - t0
     t0 = time.perf_counter()
-    _, Ih = h.search(Q, K, 64)
+    _, Ih = h.search(Q, K, 64, nthreads=nt)
     ts = time.perf_counter() - t0
     t0 = time.perf_counter()
-    _, If = orc.flat_ip_topk(X, Q, K, acc="f32")
+    _, If = orc.flat_ip_topk(X, Q, K, acc="f32", nthreads=nt)
     tf = time.perf_counter() - t0
     return {"data": kind, "n": n, "nq": nq, "M": 32, "efConstruction": 200, "efSearch": 64, "build_s": round(tb, 2),
             "hnsw_qps": round(nq / ts, 1), "flat_qps_batched": round(nq / tf, 1),
-            "recall_at_10_vs_flat": round(orc.recall_at_k(Ih, If), 4), "cores": orc.num_threads(),
+            "recall_at_10_vs_flat": round(orc.recall_at_k(Ih, If), 4), "cores": nt,
             "note": "HNSW restatement (oracle/hnsw.cpp) with the reference's parameters (src/config.py:126-139), not faiss"}
 
 
@@ -205,6 +216,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["OMP_NUM_THREADS"] = str(host_threads())   # before the OpenMP runtime of the oracle starts
     steps = max(1, args.steps)
     qps, info = cpu_flat_qps(steps, warmup=max(1, min(args.warmup, 3)))
     line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
