@@ -220,6 +220,17 @@ B2S_API int b2s_search_sharded_device(b2s_index* idx, const void* queries, int q
 B2S_API int b2s_search_sharded(b2s_index* idx, const float* queries, int64_t nq, int k, float* out_scores,
                                int64_t* out_ids);
 
+/*
+ * Replaces maxsim_aggregation (src/utils/chunk.py:123-148: max chunk score per document) for search
+ * results: scores/ids [nq, k_in] are a query's chunk hits sorted by descending score; chunk_to_doc
+ * [n_chunks] maps a chunk (row) id to its document id.  Keeps each document's best (= first) hit,
+ * in order: out_scores / out_doc_ids [nq, k_out] padded with (-FLT_MAX, -1); out_counts optional.
+ * DEVICE buffers.
+ */
+B2S_API int b2s_maxsim_device(int device, const float* scores, const int64_t* ids, int64_t nq, int k_in,
+                              const int64_t* chunk_to_doc, int64_t n_chunks, int k_out, float* out_scores,
+                              int64_t* out_doc_ids, int32_t* out_counts, void* cuda_stream);
+
 B2S_API int b2s_last_stats(const b2s_index* idx, b2s_stats* out);
 
 /*

@@ -39,7 +39,7 @@ EXPORTS = [
     "b2s_similarity", "b2s_read_rows_f32", "b2s_rows_device", "b2s_last_stats", "b2s_read_timings",
     "b2s_packed_bytes", "b2s_merge_packed_device", "b2s_score_rows_device", "b2s_ance_filter_device",
     "b2s_exchange_create", "b2s_exchange_local", "b2s_exchange_connect", "b2s_exchange_status",
-    "b2s_search_sharded_device", "b2s_search_sharded",
+    "b2s_search_sharded_device", "b2s_search_sharded", "b2s_maxsim_device",
 ]
 
 
@@ -147,6 +147,8 @@ def lib() -> ctypes.CDLL:
     L.b2s_search_sharded_device.restype = i32
     L.b2s_search_sharded.argtypes = [vp, vp, i64, i32, vp, vp]
     L.b2s_search_sharded.restype = i32
+    L.b2s_maxsim_device.argtypes = [i32, vp, vp, i64, i32, vp, i64, i32, vp, vp, vp, vp]
+    L.b2s_maxsim_device.restype = i32
     for name in ("b2s_create", "b2s_destroy", "b2s_reserve", "b2s_add_f32", "b2s_add_bf16", "b2s_dim",
                  "b2s_reset", "b2s_set_id_offset", "b2s_set_option", "b2s_search", "b2s_search_device",
                  "b2s_merge_device", "b2s_similarity", "b2s_read_rows_f32", "b2s_last_stats"):

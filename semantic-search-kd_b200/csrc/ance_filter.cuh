@@ -85,4 +85,35 @@ __global__ void ance_filter_kernel(const float* __restrict__ cand_scores, const 
     }
 }
 
+// MaxSim aggregation of chunk hits into document hits
+// (/root/reference/src/utils/chunk.py:123-148: max chunk score per document).  The chunk hits of a
+// query arrive sorted by descending score, so a document's maximum is its FIRST occurrence: keep
+// the first hit of every document, in order.  One thread per query.
+__global__ void maxsim_kernel(const float* __restrict__ scores, const long long* __restrict__ ids, long long nq, int k_in,
+                              const long long* __restrict__ chunk_to_doc, long long n_chunks, int k_out,
+                              float* __restrict__ out_scores, long long* __restrict__ out_docs,
+                              int* __restrict__ out_counts) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    long long* od = out_docs + q * k_out;
+    float* os = out_scores + q * k_out;
+    int c = 0;
+    for (int j = 0; j < k_in && c < k_out; ++j) {
+        const long long id = ids[q * k_in + j];
+        if (id < 0) break;
+        const long long doc = (id < n_chunks) ? chunk_to_doc[id] : id;
+        bool seen = false;
+        for (int t = 0; t < c; ++t) seen = seen || (od[t] == doc);
+        if (seen) continue;
+        od[c] = doc;
+        os[c] = scores[q * k_in + j];
+        ++c;
+    }
+    if (out_counts) out_counts[q] = c;
+    for (; c < k_out; ++c) {
+        od[c] = -1;
+        os[c] = -FLT_MAX;
+    }
+}
+
 }  // namespace b2s

@@ -1041,6 +1041,26 @@ B2S_API int b2s_ance_filter_device(int device, const float* cand_scores, const i
     return B2S_OK;
 }
 
+B2S_API int b2s_maxsim_device(int device, const float* scores, const int64_t* ids, int64_t nq, int k_in,
+                              const int64_t* chunk_to_doc, int64_t n_chunks, int k_out, float* out_scores,
+                              int64_t* out_doc_ids, int32_t* out_counts, void* cuda_stream) {
+    if (nq < 0 || k_in < 0 || k_out < 0 || n_chunks < 0) return fail(B2S_ERR_INVALID, "bad arguments");
+    if (nq == 0 || k_out == 0) return B2S_OK;
+    if (!out_scores || !out_doc_ids || (k_in > 0 && (!scores || !ids)) || (n_chunks > 0 && !chunk_to_doc))
+        return fail(B2S_ERR_INVALID, "null buffer");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(B2S_ERR_NO_DEVICE, "no CUDA device: libb200search has no CPU fallback");
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    maxsim_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
+        scores, reinterpret_cast<const long long*>(ids), nq, k_in, reinterpret_cast<const long long*>(chunk_to_doc), n_chunks,
+        k_out, out_scores, reinterpret_cast<long long*>(out_doc_ids), out_counts);
+    CUDA_TRY(cudaGetLastError());
+    return B2S_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // cross-GPU exchange (exchange.cuh)
 // ---------------------------------------------------------------------------------------------

@@ -50,6 +50,44 @@ def retrieve_topk(index: FlatIPIndex, query_embs, k: int):
     return index.search(query_embs, k)[1]
 
 
+def maxsim_aggregation(chunk_scores) -> Dict[str, float]:
+    """Same contract as the reference's ``maxsim_aggregation`` (``src/utils/chunk.py:123-148``):
+    ``[(chunk_id "{doc_id}_{chunk_idx}", score), ...] -> {doc_id: max score}`` (host-side, for the
+    string-keyed lists the reference passes around; the device twin is ``maxsim_topk``)."""
+    doc_scores: Dict[str, float] = {}
+    for chunk_id, score in chunk_scores:
+        doc_id = "_".join(chunk_id.split("_")[:-1]) if "_" in chunk_id else chunk_id
+        if doc_id not in doc_scores or score > doc_scores[doc_id]:
+            doc_scores[doc_id] = score
+    return doc_scores
+
+
+def maxsim_topk(index: FlatIPIndex, query_embs, k: int, chunk_to_doc, k_chunks: Optional[int] = None):
+    """Document-level top-k by MaxSim: search ``k_chunks`` (default 4k) chunk rows per query, keep each
+    document's best chunk (``b2s_maxsim_device``).  ``chunk_to_doc``: int64 ``[ntotal]``, chunk row ->
+    document id.  Returns numpy ``(doc_scores float32 [nq,k], doc_ids int64 [nq,k] (-1 padded))``."""
+    if torch is None or not torch.cuda.is_available():
+        raise IndexBuildError("maxsim_topk needs torch with CUDA (device tensors are the plumbing)")
+    dev = torch.device("cuda", index.device if index.device is not None else 0)
+    q = query_embs if isinstance(query_embs, torch.Tensor) else torch.from_numpy(
+        np.ascontiguousarray(np.atleast_2d(np.asarray(query_embs, dtype=np.float32))))
+    q = q.to(dev).contiguous()
+    c2d = chunk_to_doc if isinstance(chunk_to_doc, torch.Tensor) else torch.from_numpy(
+        np.ascontiguousarray(np.asarray(chunk_to_doc, dtype=np.int64)))
+    c2d = c2d.to(dev).contiguous()
+    k_in = min(2048, int(k_chunks) if k_chunks else 4 * int(k))
+    scores, ids = index.search_device(q, k_in)
+    nq = q.shape[0]
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_d = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _check(_lib.lib().b2s_maxsim_device(dev.index, ctypes.c_void_p(scores.data_ptr()), ctypes.c_void_p(ids.data_ptr()), nq,
+                                        k_in, ctypes.c_void_p(c2d.data_ptr()), c2d.shape[0], int(k),
+                                        ctypes.c_void_p(out_s.data_ptr()), ctypes.c_void_p(out_d.data_ptr()), None, stream),
+           "b2s_maxsim_device")
+    return out_s.cpu().numpy(), out_d.cpu().numpy()
+
+
 class ANCEMiner:
     """Stage-3 adversarial negative mining with the student's own scores."""
 

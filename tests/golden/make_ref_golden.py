@@ -13,6 +13,8 @@ What is executed (unmodified, imported from /root/reference):
   search with the full ``np.matmul(query_embs, corpus_embs.T)`` matrix.
 * ``src.mining.miners.ANCEMiner.mine``             (src/mining/miners.py:184-253) -- margin filter
   + descending sort + top-k over the candidate scores.
+* ``src.utils.chunk.maxsim_aggregation``           (src/utils/chunk.py:123-148) -- max chunk score per
+  document, applied to the chunks the reference retrieved (row r = chunk r % 3 of document r // 3).
 
 What is NOT the reference's: ``src/models/student.py`` is absent from the tree,
 so the model is a stub that returns seeded unit-norm 384-d embeddings for the strings it is given
@@ -25,7 +27,7 @@ each retrieved id in rank order (``labels[i] for i in top_k_indices``, eval.py:8
 simple_eval.py:36), so a list subclass that records ``__getitem__`` calls yields exactly the ids
 the reference retrieved, in order, for every (query, k).
 
-Outputs: tests/golden/ref_eval.npz, tests/golden/ref_ance.json (inputs are regenerated from the
+Outputs: tests/golden/ref_eval.npz, tests/golden/ref_ance.json, tests/golden/ref_maxsim.json (inputs are regenerated from the
 seeds by the tests and checked by SHA-256).
 """
 from __future__ import annotations
@@ -149,6 +151,17 @@ def main():
     for margin, top_k in ((0.1, 5), (0.02, 5), (0.3, 20)):
         negs = ANCEMiner(stub, margin=margin).mine(queries, positives, candidates, texts, texts, top_k=top_k)
         out[f"margin{margin}_top{top_k}"] = negs
+    # --- maxsim_aggregation (src/utils/chunk.py:123-148) on the reference's own retrieved chunks ----
+    from src.utils.chunk import maxsim_aggregation          # /root/reference/src/utils/chunk.py
+    Xd, Qd = X.astype(np.float64), Q.astype(np.float64)
+    maxsim = []
+    for i in range(nq):
+        hits = payload["eval_ids_k20"][i]
+        # corpus row r is chunk r % 3 of document r // 3
+        chunk_scores = [(f"doc{int(r) // 3}_{int(r) % 3}", float(Qd[i] @ Xd[int(r)])) for r in hits]
+        maxsim.append(maxsim_aggregation(chunk_scores))
+    (OUT / "ref_maxsim.json").write_text(json.dumps(maxsim) + "\n")
+
     (OUT / "ref_ance.json").write_text(json.dumps(
         {"n": n, "nq": nq, "seed_x": seed_x, "seed_q": seed_q, "positives": positives, "candidates": candidates,
          "negatives": out, "sha_X": sha(X), "sha_Q": sha(Q)}, indent=0) + "\n")

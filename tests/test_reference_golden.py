@@ -165,3 +165,39 @@ def test_cuda_corpus_wide_ance(oracle, nq, top_k):
             assert set(exp) <= set(got) <= set(exp) | maybe, (i, got, exp, maybe)
         assert np.all(np.diff(scores[i][:counts[i]]) <= 0)
     idx.close()
+
+
+def test_maxsim_mirror_matches_reference(ref_case):
+    """Host mirror of maxsim_aggregation == the reference's own function output (tests/golden/ref_maxsim.json)."""
+    import semantic_search_kd_b200 as pkg
+    X, Q, z, meta = ref_case
+    ref = json.loads((GOLDEN / "ref_maxsim.json").read_text())
+    Xd, Qd = X.astype(np.float64), Q.astype(np.float64)
+    for i in range(meta["nq"]):
+        hits = z["eval_ids_k20"][i]
+        chunk_scores = [(f"doc{int(r) // 3}_{int(r) % 3}", float(Qd[i] @ Xd[int(r)])) for r in hits]
+        assert pkg.maxsim_aggregation(chunk_scores) == ref[i]
+
+
+@pytest.mark.gpu
+def test_cuda_maxsim_matches_reference(ref_case):
+    """Device MaxSim over the CUDA search result == the reference's maxsim_aggregation over the chunks
+    the reference retrieved (same documents, scores within the bf16 tolerance)."""
+    import semantic_search_kd_b200 as pkg
+    X, Q, z, meta = ref_case
+    ref = json.loads((GOLDEN / "ref_maxsim.json").read_text())
+    idx = pkg.FlatIPIndex(384, metric="inner_product")
+    idx.add(X)
+    chunk_to_doc = np.arange(len(X), dtype=np.int64) // 3
+    S, D = pkg.maxsim_topk(idx, Q, 20, chunk_to_doc, k_chunks=20)
+    for i in range(meta["nq"]):
+        got = {f"doc{int(d)}": float(s) for s, d in zip(S[i], D[i]) if d >= 0}
+        exp = ref[i]
+        kth = min(exp.values())
+        for doc in set(got) ^ set(exp):                      # only near-ties of the 20th chunk may differ
+            s = got.get(doc, exp.get(doc))
+            assert abs(s - kth) <= 2e-3, (i, doc, s, kth)
+        for doc in set(got) & set(exp):
+            assert abs(got[doc] - exp[doc]) <= 1e-3, (i, doc)
+        assert list(S[i][:len(got)]) == sorted(S[i][:len(got)], reverse=True)
+    idx.close()
