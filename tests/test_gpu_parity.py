@@ -489,3 +489,33 @@ def test_tensor_small_batch_both_mma_shapes(pkg, oracle, single):
         check(oracle, idx, X, q, k, q_bf16=True)
         assert idx.stats()["path"] == 2
     idx.close()
+
+
+def test_randomised_shapes_auto_path(pkg, oracle):
+    """Seeded sweep over (rows, queries, k, metric, duplicates) with the default kernel choice: whatever
+    combination of scan / single-CTA / pair kernels, seeding, shared thresholds and merges a shape
+    selects must satisfy the parity rule."""
+    rng = np.random.default_rng(20260101)
+    for case in range(36):
+        n = int(rng.choice([1, 7, 255, 256, 257, 1000, 4097, 20000, 65536, 150001]))
+        nq = int(rng.choice([1, 2, 3, 4, 17, 128, 129, 255, 256, 257, 513]))
+        k = int(rng.choice([1, 2, 10, 31, 32, 33, 100, 257, 1000]))
+        cosine = bool(rng.integers(0, 2))
+        X, Q = unit_rows(n, 384, 1000 + case), unit_rows(nq, 384, 2000 + case)
+        if n > 600 and rng.integers(0, 2):
+            X[n // 3:n // 3 + 40] = X[5]                      # a block of exact duplicates
+            Q[0] = X[5]
+        if cosine:                                            # un-normalised inputs, cosine metric
+            Xr = (X * rng.uniform(0.5, 2.0, (n, 1))).astype(np.float32)
+            Qr = (Q * rng.uniform(0.5, 2.0, (nq, 1))).astype(np.float32)
+            idx = build(pkg, Xr, metric="cosine")
+            D, I = idx.search(Qr, k)
+        else:
+            idx = build(pkg, X)
+            D, I = idx.search(Q, k)
+        Dr, Ir = oracle.flat_ip_topk(X, Q, k)
+        rep = oracle.compare_topk(D, I, Dr, Ir, X, Q, tie_tol=TIE_TOL_BF16)
+        assert rep["ok"] and rep["max_abs_score_err"] <= TIE_TOL_BF16, (case, n, nq, k, cosine, rep)
+        valid = I >= 0
+        assert (valid.sum(axis=1) == min(k, n)).all(), (case, n, nq, k)
+        idx.close()
