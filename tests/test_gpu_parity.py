@@ -519,3 +519,32 @@ def test_randomised_shapes_auto_path(pkg, oracle):
         valid = I >= 0
         assert (valid.sum(axis=1) == min(k, n)).all(), (case, n, nq, k)
         idx.close()
+
+
+@pytest.mark.parametrize("nq,k", [(1, 10), (64, 10), (300, 100)])
+def test_search_is_cuda_graph_capturable(pkg, oracle, nq, k):
+    """Once the workspace is warm a device search allocates nothing and only enqueues work on the
+    caller's stream, so it can be captured in a CUDA graph and replayed on new query contents."""
+    import torch
+    X = unit_rows(60000, 384, 161)
+    dev = torch.device("cuda", 0)
+    idx = build(pkg, X)
+    q = torch.from_numpy(unit_rows(nq, 384, 162)).to(dev)
+    out = (torch.empty((nq, k), dtype=torch.float32, device=dev), torch.empty((nq, k), dtype=torch.int64, device=dev))
+    idx.search_device(q, k, out=out)                     # warm: workspaces, function attributes, tensor maps
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            idx.search_device(q, k, out=out)
+    for rep in range(3):
+        Qn = unit_rows(nq, 384, 170 + rep)
+        q.copy_(torch.from_numpy(Qn).to(dev))
+        g.replay()
+        torch.cuda.synchronize()
+        Dr, Ir = oracle.flat_ip_topk(X, Qn, k)
+        repo = oracle.compare_topk(out[0].cpu().numpy(), out[1].cpu().numpy(), Dr, Ir, X, Qn, tie_tol=TIE_TOL_BF16)
+        assert repo["ok"], (rep, repo)
+    idx.close()
