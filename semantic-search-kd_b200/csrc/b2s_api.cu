@@ -444,7 +444,9 @@ int search_core(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, in
 #ifdef B2S_NO_TENSOR_PATH
     path = B2S_PATH_SCAN;
 #else
-    if (path == B2S_PATH_AUTO) path = (nq >= idx->opt_tc_min_nq) ? B2S_PATH_TENSOR : B2S_PATH_SCAN;
+    // batches go to the tensor path; so do 1-2 queries with a large k (the scan kernel's shared-memory lists
+    // are tuned for small k: 3.0 ms at k = 1000 vs 1.2 ms on the single-CTA tensor variant)
+    if (path == B2S_PATH_AUTO) path = (nq >= idx->opt_tc_min_nq || k >= 256) ? B2S_PATH_TENSOR : B2S_PATH_SCAN;
     if (path == B2S_PATH_TENSOR && !tensor_path_supported(idx->dim)) path = B2S_PATH_SCAN;
 #endif
     idx->stats.path = path;
