@@ -420,6 +420,8 @@ def run_ours(args):
     sh, ih = idx.search(Qh[5:6], K)
     agree = bool(np.array_equal(idd.cpu().numpy(), ih))
 
+    ex_status = idx.exchange_status() if world > 1 and hasattr(idx, "exchange_status") else 0
+    exchange = getattr(idx, "exchange", None) if world > 1 else None   # may have fallen back to nccl
     if rank == 0:
         peak, peak_src = peaks()
         local_bytes = (hi - lo) * DIM * 2   # rank 0's shard (ranges differ by at most one row)
@@ -458,7 +460,7 @@ def run_ours(args):
                                       "the scan of query i+1 overlap the merge/exchange of query i; needs a query buffer "
                                       "that is not written by the immediately preceding kernel)"},
                 "gpu_launches": launches_per_step * args.steps,
-                "clocks": clk, "build_s": round(t_build, 2), "paths_agree": agree}
+                "clocks": clk, "build_s": round(t_build, 2), "paths_agree": agree, "exchange_timeouts": ex_status}
         if n_gpus == 1 and not args.no_batched:
             try:
                 line["batched"] = batched_report(torch, local, dev)

@@ -80,6 +80,7 @@ class ShardedFlatIPIndex:
         self._ex_slot_bytes = int(exchange_slot_bytes)
         self._ex_max_nq = int(exchange_max_nq)
         self._ex_ready = False
+        self.exchange_fallback_reason = None
         self.n_total = 0
         self.range = (0, 0)
         self._bufs = {}
@@ -130,15 +131,28 @@ class ShardedFlatIPIndex:
         L = _lib.lib()
         h = self.local._ensure()
         handle = (ctypes.c_ubyte * 64)()
-        _check(L.b2s_exchange_create(h, self.world, self.rank, self._ex_slot_bytes, self._ex_max_nq, handle),
-               "b2s_exchange_create")
+        rc = L.b2s_exchange_create(h, self.world, self.rank, self._ex_slot_bytes, self._ex_max_nq, handle)
         mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
         allh = torch.empty((self.world * 64,), dtype=torch.uint8, device=device)
         dist.all_gather_into_tensor(allh, mine, group=self.group)
-        buf = np.ascontiguousarray(allh.cpu().numpy())
-        _check(L.b2s_exchange_connect(h, buf.ctypes.data_as(ctypes.c_void_p), 0), "b2s_exchange_connect")
-        dist.barrier(group=self.group)   # every rank has mapped every buffer before anyone pushes
-        self._ex_ready = True
+        if rc == _lib.B2S_OK:
+            buf = np.ascontiguousarray(allh.cpu().numpy())
+            rc = L.b2s_exchange_connect(h, buf.ctypes.data_as(ctypes.c_void_p), 0)
+        # every rank must end up on the same protocol: if any rank could not map its peers (no P2P / IPC on
+        # this box) all of them use the NCCL all-gather instead
+        ok = torch.tensor([1 if rc == _lib.B2S_OK else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)   # also: every buffer is mapped before a push
+        if int(ok.item()) == 1:
+            self._ex_ready = True
+        else:
+            self.exchange = "nccl"
+            self.exchange_fallback_reason = _lib.last_error() if rc != _lib.B2S_OK else "a peer rank could not map the buffers"
+
+    def exchange_status(self) -> int:
+        """0, or the sequence number of a sharded call whose wait for a peer timed out (synchronises)."""
+        if not self._ex_ready:
+            return 0
+        return int(_lib.lib().b2s_exchange_status(self.local._h))
 
     def _peer_ok(self, nq: int, k: int) -> bool:
         return (self.exchange == "peer" and self.world > 1 and nq <= self._ex_max_nq and
@@ -149,9 +163,9 @@ class ShardedFlatIPIndex:
         if self.n_total == 0 and self.local.ntotal == 0 and self.local._h is None:
             raise IndexNotBuiltError()
         nq = q.shape[0]
+        if nq and k and self._peer_ok(nq, k) and not self._ex_ready:
+            self._connect_exchange(q.device)
         if nq and k and self._peer_ok(nq, k):
-            if not self._ex_ready:
-                self._connect_exchange(q.device)
             if q.dtype not in (torch.float32, torch.bfloat16):
                 q = q.float()
             q = q.contiguous()
@@ -193,9 +207,9 @@ class ShardedFlatIPIndex:
             q = q.reshape(1, -1)
         dev = torch.device("cuda", self.local.device if self.local.device is not None else torch.cuda.current_device())
         nq = q.shape[0]
+        if nq and k and self._peer_ok(nq, k) and not self._ex_ready:
+            self._connect_exchange(dev)
         if nq and k and self._peer_ok(nq, k):
-            if not self._ex_ready:
-                self._connect_exchange(dev)
             scores = np.empty((nq, k), dtype=np.float32)
             ids = np.empty((nq, k), dtype=np.int64)
             _check(_lib.lib().b2s_search_sharded(self.local._h, q.ctypes.data_as(ctypes.c_void_p), nq, int(k),
