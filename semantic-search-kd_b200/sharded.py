@@ -59,7 +59,8 @@ class ShardedFlatIPIndex:
     def __init__(self, embedding_dim: int = 384, metric: str = "cosine", group=None,
                  local_index: Optional[FlatIPIndex] = None,
                  merge_fn: Optional[Callable] = None, device: Optional[int] = None,
-                 exchange: str = "auto", exchange_slot_bytes: int = 4 << 20, exchange_max_nq: int = 16384) -> None:
+                 exchange: str = "auto", exchange_slot_bytes: int = 4 << 20, exchange_max_nq: int = 16384,
+                 shard: str = "corpus") -> None:
         if dist is None or not dist.is_initialized():
             raise IndexBuildError("torch.distributed must be initialised before ShardedFlatIPIndex")
         self.group = group
@@ -69,6 +70,12 @@ class ShardedFlatIPIndex:
         self.local = local_index if local_index is not None else FlatIPIndex(embedding_dim, metric=metric,
                                                                               device=device)
         self._merge_fn = merge_fn
+        if shard not in ("corpus", "queries"):
+            raise IndexBuildError("shard must be 'corpus' or 'queries'")
+        # shard="queries": every rank holds the WHOLE corpus and searches its slice of the query batch; the
+        # only traffic is the all-gather of the answers.  For sweeps whose corpus fits one GPU (ANCE mining
+        # over 8.8M rows = 6.8 GB): no candidate exchange, no merge, same FLOPs.
+        self.shard = shard
         if exchange not in ("auto", "peer", "nccl"):
             raise IndexBuildError("exchange must be 'auto', 'peer' or 'nccl'")
         # the fused peer-memory exchange needs real GPUs and the CUDA merge (not the injected test doubles)
@@ -89,6 +96,11 @@ class ShardedFlatIPIndex:
     def build_from_embeddings(self, embeddings, n_total: Optional[int] = None) -> "ShardedFlatIPIndex":
         """Every rank passes the FULL array (or only needs its slice to be valid); each keeps its range."""
         n = int(n_total if n_total is not None else embeddings.shape[0])
+        if self.shard == "queries":
+            self.local.build_from_embeddings(embeddings)
+            self.local.set_id_offset(0)
+            self.n_total, self.range = n, (0, n)
+            return self
         lo, hi = shard_range(n, self.world, self.rank)
         self.local.build_from_embeddings(embeddings[lo:hi])
         self.local.set_id_offset(lo)
@@ -163,6 +175,8 @@ class ShardedFlatIPIndex:
         if self.n_total == 0 and self.local.ntotal == 0 and self.local._h is None:
             raise IndexNotBuiltError()
         nq = q.shape[0]
+        if self.shard == "queries":
+            return self._search_query_sharded(q, k)
         if nq and k and self._peer_ok(nq, k) and not self._ex_ready:
             self._connect_exchange(q.device)
         if nq and k and self._peer_ok(nq, k):
@@ -197,6 +211,22 @@ class ShardedFlatIPIndex:
                    "b2s_merge_packed_device")
         return out_s, out_i
 
+    def _search_query_sharded(self, q: "torch.Tensor", k: int):
+        """Rank r searches queries [r*ceil(nq/G), ...) against its full copy of the corpus; one all-gather
+        of the (padded) answers gives every rank all of them."""
+        nq = q.shape[0]
+        per = -(-nq // self.world) if nq else 0
+        lo, hi = min(nq, self.rank * per), min(nq, self.rank * per + per)
+        s_all = torch.empty((self.world, per, k), dtype=torch.float32, device=q.device)
+        i_all = torch.empty((self.world, per, k), dtype=torch.int64, device=q.device)
+        mine_s, mine_i = s_all[self.rank], i_all[self.rank]
+        if hi > lo:
+            self.local.search_device(q[lo:hi].contiguous(), k, out=(mine_s[: hi - lo], mine_i[: hi - lo]))
+        if self.world > 1 and per:
+            dist.all_gather_into_tensor(s_all.view(-1), mine_s.reshape(-1), group=self.group)
+            dist.all_gather_into_tensor(i_all.view(-1), mine_i.reshape(-1), group=self.group)
+        return s_all.view(-1, k)[:nq], i_all.view(-1, k)[:nq]
+
     def search(self, query_emb, k: int = 10):
         """``search(query_emb, k) -> (scores, ids)``: numpy in -> numpy out (H2D / D2H inside),
         CUDA tensor in -> CUDA tensors out.  Every rank must call it with the same queries."""
@@ -207,6 +237,10 @@ class ShardedFlatIPIndex:
             q = q.reshape(1, -1)
         dev = torch.device("cuda", self.local.device if self.local.device is not None else torch.cuda.current_device())
         nq = q.shape[0]
+        if self.shard == "queries":
+            qd = torch.from_numpy(q).to(dev) if dev.type == "cuda" else torch.from_numpy(q)
+            s, i = self._search_query_sharded(qd, k)
+            return s.cpu().numpy(), i.cpu().numpy()
         if nq and k and self._peer_ok(nq, k) and not self._ex_ready:
             self._connect_exchange(dev)
         if nq and k and self._peer_ok(nq, k):

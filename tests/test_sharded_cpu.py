@@ -126,3 +126,33 @@ def test_shard_ranges_cover_exactly():
             assert rs[0][0] == 0 and rs[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
             assert all(hi >= lo for lo, hi in rs)
+
+
+def _worker_queries(rank, world, port, n, nq, k, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from conftest import unit_rows
+        from oracle import oracle as orc
+        from semantic_search_kd_b200.sharded import ShardedFlatIPIndex
+        X, Q = unit_rows(n, 384, 15), unit_rows(nq, 384, 16)
+        idx = ShardedFlatIPIndex(384, metric="inner_product", local_index=OracleLocalIndex(384),
+                                 merge_fn=oracle_merge, shard="queries")
+        idx.build_from_embeddings(X)
+        assert idx.local.ntotal == n and idx.range == (0, n)          # the whole corpus on every rank
+        s, i = idx.search_device(torch.from_numpy(Q), k)
+        Dr, Ir = orc.flat_ip_topk(orc.round_bf16(X), Q, k)
+        ret[rank] = bool(np.array_equal(i.numpy(), Ir) and np.allclose(s.numpy(), Dr, atol=1e-6) and s.shape == (nq, k))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,nq,k", [(800, 7, 10), (800, 1, 5), (50, 4, 10)])
+def test_query_sharded_search_world2_gloo(n, nq, k):
+    """shard="queries": replicated corpus, each rank searches its slice of the batch, answers all-gathered."""
+    world = 2
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_queries, args=(world, port, n, nq, k, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
