@@ -145,7 +145,10 @@ struct b2s_index {
     const ExchangeArgs* ex_call = nullptr;
     int ex_fused = 0;
     unsigned* done_counter = nullptr;   // device word for the scan kernel's fused merge tail
+    const float* host_q = nullptr;      // host-buffer call in flight: its queries may ride in the kernel parameters
     int opt_fused_tail = 1;
+    int opt_host_inline = 1;            // host-buffer calls of 1-2 queries: query in the kernel parameters, answer
+                                        // written straight to pinned host memory (no copy-engine operations)
     int opt_exchange_ll = 1;            // fused exchange: tagged 8-byte words instead of payload + fence + flag
 #ifndef B2S_NO_TENSOR_PATH
     TensorPathState tc;
@@ -284,7 +287,7 @@ int launch_merge(const b2s_index* idx, const MergeParams& mp, int nq, int q_offs
 
 // Scan path for queries [0, nq) already in fp32 on the device.
 int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* out_scores,
-                int64_t* out_ids, cudaStream_t s, bool seed, bool late_wait_ok) {
+                int64_t* out_ids, cudaStream_t s, bool seed, bool late_wait_ok, const float* inline_q) {
     const int cap = list_capacity(k);
     const int rpi = scan_rows_per_iter(idx->dim);
     const int unit = rpi * kScanWarps;
@@ -326,6 +329,11 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
                 // The scan only READS the corpus and the caller's queries unless a kernel of THIS call
                 // ran before it (query prep, seeding pass, an earlier group writing the same workspace).
                 p.pdl_late_wait = (late_wait_ok && !seed && nq <= max_group) ? 1 : 0;
+                p.use_inline = 0;
+                if (inline_q != nullptr) {
+                    p.use_inline = 1;
+                    memcpy(p.q_inline, inline_q, (size_t)nq * idx->dim * sizeof(float));
+                }
                 p.fused_tail = 0;
                 if (fuse_tail) {
                     p.fused_tail = idx->ex_call ? 2 : 1;
@@ -381,6 +389,20 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
                   int64_t* out_ids, cudaStream_t s, bool seed, bool normalize);
 void tensor_path_release(b2s_index* idx);
 #endif
+
+// kernel family of a search
+int choose_path(const b2s_index* idx, int64_t nq, int k) {
+    int path = idx->opt_path;
+#ifdef B2S_NO_TENSOR_PATH
+    path = B2S_PATH_SCAN;
+#else
+    // batches go to the tensor path; so do 1-2 queries with a large k (the scan kernel's shared-memory lists
+    // are tuned for small k: 3.0 ms at k = 1000 vs 1.2 ms on the single-CTA tensor variant)
+    if (path == B2S_PATH_AUTO) path = (nq >= idx->opt_tc_min_nq || k >= 256) ? B2S_PATH_TENSOR : B2S_PATH_SCAN;
+    if (path == B2S_PATH_TENSOR && !tensor_path_supported(idx->dim)) path = B2S_PATH_SCAN;
+#endif
+    return path;
+}
 
 int search_core(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, int k, float* out_scores,
                 int64_t* out_ids, cudaStream_t s) {
@@ -439,16 +461,7 @@ int search_core(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, in
         return B2S_OK;
     }
 
-    // kernel family
-    int path = idx->opt_path;
-#ifdef B2S_NO_TENSOR_PATH
-    path = B2S_PATH_SCAN;
-#else
-    // batches go to the tensor path; so do 1-2 queries with a large k (the scan kernel's shared-memory lists
-    // are tuned for small k: 3.0 ms at k = 1000 vs 1.2 ms on the single-CTA tensor variant)
-    if (path == B2S_PATH_AUTO) path = (nq >= idx->opt_tc_min_nq || k >= 256) ? B2S_PATH_TENSOR : B2S_PATH_SCAN;
-    if (path == B2S_PATH_TENSOR && !tensor_path_supported(idx->dim)) path = B2S_PATH_SCAN;
-#endif
+    const int path = choose_path(idx, nq, k);
     idx->stats.path = path;
     const bool normalize = idx->metric == B2S_METRIC_COSINE;
     // Threshold seeding: on the scan path a pre-pass over every 64th unit pays for itself once the
@@ -460,7 +473,24 @@ int search_core(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, in
 
     if (path == B2S_PATH_SCAN) {
         const float* qf = reinterpret_cast<const float*>(queries);
-        if (q_dtype != B2S_DTYPE_F32 || normalize) {
+        // host-buffer call of 1-2 queries: they travel in the scan kernel's parameters (normalised here for cosine)
+        float inline_buf[kScanInlineFloats];
+        const float* inline_q = nullptr;
+        if (idx->host_q != nullptr && q_dtype == B2S_DTYPE_F32 && nq * idx->dim <= kScanInlineFloats &&
+            nq <= scan_max_nq(idx->dim)) {
+            inline_q = idx->host_q;
+            if (normalize) {
+                for (int64_t qi = 0; qi < nq; ++qi) {
+                    const float* src = idx->host_q + qi * idx->dim;
+                    float ss = 0.f;
+                    for (int i = 0; i < idx->dim; ++i) ss = fmaf(src[i], src[i], ss);
+                    const float scale = ss > 0.f ? 1.0f / sqrtf(ss) : 0.f;
+                    for (int i = 0; i < idx->dim; ++i) inline_buf[qi * idx->dim + i] = src[i] * scale;
+                }
+                inline_q = inline_buf;
+            }
+        }
+        if (inline_q == nullptr && (q_dtype != B2S_DTYPE_F32 || normalize)) {
             if ((rc = idx->ws_qf32.ensure((size_t)nq * idx->dim * sizeof(float))) != B2S_OK) return rc;
             const int warps = 8;
             prep_queries_kernel<<<(unsigned)((nq + warps - 1) / warps), warps * 32, 0, s>>>(
@@ -474,7 +504,7 @@ int search_core(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, in
         // late PDL wait only if no kernel of this call precedes the scan and no event sits between
         // consecutive calls' kernels (timing on) -- see scan_topk.cuh
         const bool late_wait_ok = (qf == reinterpret_cast<const float*>(queries)) && idx->opt_pdl == 2;
-        rc = search_scan(idx, qf, nq, k, out_scores, out_ids, s, seed, late_wait_ok);
+        rc = search_scan(idx, qf, nq, k, out_scores, out_ids, s, seed, late_wait_ok, inline_q);
         if (rc != B2S_OK) return rc;
     } else {
 #ifndef B2S_NO_TENSOR_PATH
@@ -771,6 +801,8 @@ B2S_API int b2s_set_option(b2s_index* idx, const char* name, int64_t value) {
         idx->opt_tc_min_nq = (int)std::max<int64_t>(1, value);
     } else if (s == "exchange_ll") {
         idx->opt_exchange_ll = value ? 1 : 0;
+    } else if (s == "host_inline") {
+        idx->opt_host_inline = value ? 1 : 0;
     } else if (s == "fused_tail") {
         idx->opt_fused_tail = value ? 1 : 0;
     } else if (s == "pdl") {
@@ -820,13 +852,16 @@ B2S_API int b2s_search_device(b2s_index* idx, const void* queries, int q_dtype, 
     return search_impl(idx, queries, q_dtype, nq, k, out_scores, out_ids, reinterpret_cast<cudaStream_t>(cuda_stream));
 }
 
-B2S_API int b2s_search(b2s_index* idx, const float* queries, int64_t nq, int k, float* out_scores,
-                       int64_t* out_ids) {
-    if (!idx) return fail(B2S_ERR_INVALID, "null index");
-    if (nq < 0 || k < 0) return fail(B2S_ERR_INVALID, "nq and k must be >= 0");
-    if (nq == 0 || k == 0) return B2S_OK;
-    if (!queries || !out_scores || !out_ids) return fail(B2S_ERR_INVALID, "null buffer");
-    std::lock_guard<std::mutex> g(idx->mu);
+// Host-buffer search shared by b2s_search and b2s_search_sharded.  Three regimes:
+//  * tiny (1-2 queries on the scan path, <= 4 KB of results): the query rides in the kernel parameters and the
+//    kernel writes the answer straight into mapped pinned host memory -- no copy-engine operation at all;
+//  * small (<= 1 MB each way): staged through pinned memory, one H2D and one D2H copy;
+//  * large: copies straight from / to the caller's (pageable) buffers.
+static int search_sharded_impl(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, int k, float* out_scores,
+                               int64_t* out_ids, void* cuda_stream, int phase);
+
+static int search_host(b2s_index* idx, const float* queries, int64_t nq, int k, float* out_scores, int64_t* out_ids,
+                       bool sharded) {
     int rc = use_device(idx);
     if (rc != B2S_OK) return rc;
     const size_t qbytes = (size_t)nq * idx->dim * sizeof(float);
@@ -834,23 +869,36 @@ B2S_API int b2s_search(b2s_index* idx, const float* queries, int64_t nq, int k, 
     const size_t ibytes = (size_t)nq * k * sizeof(int64_t);
     if ((rc = idx->ws_io_q.ensure(qbytes)) != B2S_OK) return rc;
     if ((rc = idx->ws_io_ids.ensure(ibytes + sbytes)) != B2S_OK) return rc;   // [ids | scores]: one D2H copy
+    int64_t* io_ids = reinterpret_cast<int64_t*>(idx->ws_io_ids.p);
     float* io_scores = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(idx->ws_io_ids.p) + ibytes);
     const bool small = qbytes <= ((size_t)1 << 20) && (sbytes + ibytes) <= ((size_t)1 << 20);
+    // (not with fp32 re-ranking: it searches k + pad candidates, possibly on another path, and re-reads the query)
+    const bool tiny = idx->opt_host_inline && idx->n > 0 && !(idx->opt_keep_f32 && idx->rows_f32) &&
+                      choose_path(idx, nq, k) == B2S_PATH_SCAN &&
+                      nq <= scan_max_nq(idx->dim) && nq * idx->dim <= kScanInlineFloats && (sbytes + ibytes) <= 4096;
+    unsigned char* po = nullptr;
     if (small) {
+        if ((rc = ensure_pinned(&idx->pin_out, &idx->pin_out_bytes, sbytes + ibytes)) != B2S_OK) return rc;
+        po = reinterpret_cast<unsigned char*>(idx->pin_out);
+    }
+    if (tiny) {
+        idx->host_q = queries;                                     // read at launch time, inside this call
+        io_ids = reinterpret_cast<int64_t*>(po);                   // pinned host memory is device-accessible (UVA)
+        io_scores = reinterpret_cast<float*>(po + ibytes);
+    } else if (small) {
         // stage through pinned memory so that both copies are truly asynchronous DMA
         if ((rc = ensure_pinned(&idx->pin_q, &idx->pin_q_bytes, qbytes)) != B2S_OK) return rc;
-        if ((rc = ensure_pinned(&idx->pin_out, &idx->pin_out_bytes, sbytes + ibytes)) != B2S_OK) return rc;
         memcpy(idx->pin_q, queries, qbytes);
         CUDA_TRY(cudaMemcpyAsync(idx->ws_io_q.p, idx->pin_q, qbytes, cudaMemcpyHostToDevice, idx->stream));
     } else {
         CUDA_TRY(cudaMemcpyAsync(idx->ws_io_q.p, queries, qbytes, cudaMemcpyHostToDevice, idx->stream));
     }
-    rc = search_impl(idx, idx->ws_io_q.p, B2S_DTYPE_F32, nq, k, io_scores,
-                     reinterpret_cast<int64_t*>(idx->ws_io_ids.p), idx->stream);
+    rc = sharded ? search_sharded_impl(idx, idx->ws_io_q.p, B2S_DTYPE_F32, nq, k, io_scores, io_ids, idx->stream, 0)
+                 : search_impl(idx, idx->ws_io_q.p, B2S_DTYPE_F32, nq, k, io_scores, io_ids, idx->stream);
+    idx->host_q = nullptr;
     if (rc != B2S_OK) return rc;
     if (small) {
-        unsigned char* po = reinterpret_cast<unsigned char*>(idx->pin_out);
-        CUDA_TRY(cudaMemcpyAsync(po, idx->ws_io_ids.p, ibytes + sbytes, cudaMemcpyDeviceToHost, idx->stream));
+        if (!tiny) CUDA_TRY(cudaMemcpyAsync(po, idx->ws_io_ids.p, ibytes + sbytes, cudaMemcpyDeviceToHost, idx->stream));
         CUDA_TRY(cudaStreamSynchronize(idx->stream));
         memcpy(out_ids, po, ibytes);
         memcpy(out_scores, po + ibytes, sbytes);
@@ -860,6 +908,16 @@ B2S_API int b2s_search(b2s_index* idx, const float* queries, int64_t nq, int k, 
         CUDA_TRY(cudaStreamSynchronize(idx->stream));
     }
     return B2S_OK;
+}
+
+B2S_API int b2s_search(b2s_index* idx, const float* queries, int64_t nq, int k, float* out_scores,
+                       int64_t* out_ids) {
+    if (!idx) return fail(B2S_ERR_INVALID, "null index");
+    if (nq < 0 || k < 0) return fail(B2S_ERR_INVALID, "nq and k must be >= 0");
+    if (nq == 0 || k == 0) return B2S_OK;
+    if (!queries || !out_scores || !out_ids) return fail(B2S_ERR_INVALID, "null buffer");
+    std::lock_guard<std::mutex> g(idx->mu);
+    return search_host(idx, queries, nq, k, out_scores, out_ids, false);
 }
 
 B2S_API int b2s_merge_device(int device, const float* scores, const int64_t* ids, int g, int64_t nq,
@@ -1201,27 +1259,7 @@ B2S_API int b2s_search_sharded(b2s_index* idx, const float* queries, int64_t nq,
     if (nq == 0 || k == 0) return B2S_OK;
     if (!queries || !out_scores || !out_ids) return fail(B2S_ERR_INVALID, "null buffer");
     std::lock_guard<std::mutex> g(idx->mu);
-    int rc = use_device(idx);
-    if (rc != B2S_OK) return rc;
-    const size_t qbytes = (size_t)nq * idx->dim * sizeof(float);
-    const size_t sbytes = (size_t)nq * k * sizeof(float);
-    const size_t ibytes = (size_t)nq * k * sizeof(int64_t);
-    if ((rc = idx->ws_io_q.ensure(qbytes)) != B2S_OK) return rc;
-    if ((rc = idx->ws_io_ids.ensure(ibytes + sbytes)) != B2S_OK) return rc;   // [ids | scores]: one D2H copy
-    float* io_scores = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(idx->ws_io_ids.p) + ibytes);
-    if ((rc = ensure_pinned(&idx->pin_q, &idx->pin_q_bytes, qbytes)) != B2S_OK) return rc;
-    if ((rc = ensure_pinned(&idx->pin_out, &idx->pin_out_bytes, sbytes + ibytes)) != B2S_OK) return rc;
-    memcpy(idx->pin_q, queries, qbytes);
-    CUDA_TRY(cudaMemcpyAsync(idx->ws_io_q.p, idx->pin_q, qbytes, cudaMemcpyHostToDevice, idx->stream));
-    rc = search_sharded_impl(idx, idx->ws_io_q.p, B2S_DTYPE_F32, nq, k, io_scores,
-                             reinterpret_cast<int64_t*>(idx->ws_io_ids.p), idx->stream, 0);
-    if (rc != B2S_OK) return rc;
-    unsigned char* po = reinterpret_cast<unsigned char*>(idx->pin_out);
-    CUDA_TRY(cudaMemcpyAsync(po, idx->ws_io_ids.p, ibytes + sbytes, cudaMemcpyDeviceToHost, idx->stream));
-    CUDA_TRY(cudaStreamSynchronize(idx->stream));
-    memcpy(out_ids, po, ibytes);
-    memcpy(out_scores, po + ibytes, sbytes);
-    return B2S_OK;
+    return search_host(idx, queries, nq, k, out_scores, out_ids, true);
 }
 
 B2S_API int b2s_last_stats(const b2s_index* idx, b2s_stats* out) {

@@ -23,6 +23,7 @@ namespace b2s {
 
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kScanInlineFloats = 768;   // queries of a host call travel inside the kernel parameters (<= 3 KB)
 
 struct ScanParams {
     const uint4* corpus;   // bf16 rows, row-major, dim*2 bytes each (16-byte aligned)
@@ -47,6 +48,10 @@ struct ScanParams {
     unsigned* done_counter;   // zero before the launch; the last CTA resets it
     MergeParams mp;
     ExchangeArgs ex;
+    // Host-buffer searches of 1-2 queries: the query rides in the kernel parameters (constant bank) -- no
+    // staging copy, no H2D operation in front of the kernel.
+    int use_inline;
+    alignas(16) float q_inline[kScanInlineFloats];
 };
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
@@ -72,7 +77,7 @@ __device__ __forceinline__ float dot8(const uint4& w, const float* q, float acc)
 // CPL = 16-byte chunks per lane = dim / 128; NQ = queries held in registers; U = row pairs in flight.
 template <int CPL, int NQ, int U>
 __global__ void __launch_bounds__(kScanThreads, (NQ <= 2 ? 2 : 1))
-scan_topk_kernel(const ScanParams p) {
+scan_topk_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* entries = reinterpret_cast<u64*>(smem_raw);  // [NQ][cap]
     __shared__ u64 s_thr_key[NQ];
@@ -102,11 +107,12 @@ scan_topk_kernel(const ScanParams p) {
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
         const int qi = p.q_begin + (q < p.nq_valid ? q : 0);
-        const float4* qp = reinterpret_cast<const float4*>(p.queries + (size_t)qi * (CPL * 128));
+        const float* qbase = p.use_inline ? p.q_inline : p.queries;   // parameter space or global memory
+        const float4* qp = reinterpret_cast<const float4*>(qbase + (size_t)qi * (CPL * 128));
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
-            float4 a = __ldg(qp + (hl + 16 * j) * 2);
-            float4 b = __ldg(qp + (hl + 16 * j) * 2 + 1);
+            float4 a = qp[(hl + 16 * j) * 2];
+            float4 b = qp[(hl + 16 * j) * 2 + 1];
             qreg[q][j][0] = a.x; qreg[q][j][1] = a.y; qreg[q][j][2] = a.z; qreg[q][j][3] = a.w;
             qreg[q][j][4] = b.x; qreg[q][j][5] = b.y; qreg[q][j][6] = b.z; qreg[q][j][7] = b.w;
         }
