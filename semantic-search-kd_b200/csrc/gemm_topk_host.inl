@@ -54,13 +54,15 @@ cudaError_t tc_launch(int ctas, size_t smem, cudaStream_t s, const CUtensorMap& 
     cfg.blockDim = dim3(kTcThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = PAIR ? 2 : 1;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // the kernel calls grid_dep_wait() itself
+    at[1].val.programmaticStreamSerializationAllowed = g_pdl_enabled ? 1 : 0;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     return cudaLaunchKernelEx(&cfg, gemm_topk_kernel<PREPASS, PAIR>, corpus, queries, p);
 }
 
@@ -139,6 +141,23 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
         const int qblocks = (cn + qblock - 1) / qblock;
         const int nq_pad = qblocks * qblock;
 
+        // workspace first, so that the list state can be zeroed BEFORE the kernels of this round: they then
+        // follow one another without a memset in between and chain through programmatic dependent launch
+        const size_t n_state = (size_t)num_lists * nq_pad;
+        if ((rc = idx->ws_lists.ensure(n_state * cap * sizeof(u64))) != B2S_OK) return rc;
+        if ((rc = idx->ws_counts.ensure(n_state * sizeof(int))) != B2S_OK) return rc;
+        if ((rc = idx->ws_thr.ensure(n_state * sizeof(u64))) != B2S_OK) return rc;
+        if ((rc = idx->ws_seed.ensure((size_t)nq_pad * sizeof(u64))) != B2S_OK) return rc;
+        if (sample_tiles > 0 && (rc = idx->ws_gmax.ensure((size_t)nq_pad * groups * sizeof(float))) != B2S_OK) return rc;
+        // shared-threshold state: [hist nq_pad*64 | gthr nq_pad] u32 (zeroed per call) + hcfg
+        const bool shared_thr = sample_tiles > 0 && idx->opt_tc_shared_thr != 0;
+        const size_t hist_words = (size_t)nq_pad * (kTcHistBins + 1);
+        if (shared_thr && (rc = idx->ws_hist.ensure(hist_words * sizeof(unsigned))) != B2S_OK) return rc;
+        if (shared_thr && (rc = idx->ws_hcfg.ensure((size_t)nq_pad * sizeof(uint2))) != B2S_OK) return rc;
+        CUDA_TRY(cudaMemsetAsync(idx->ws_counts.p, 0, n_state * sizeof(int), s));
+        CUDA_TRY(cudaMemsetAsync(idx->ws_thr.p, 0, n_state * sizeof(u64), s));
+        if (shared_thr) CUDA_TRY(cudaMemsetAsync(idx->ws_hist.p, 0, hist_words * sizeof(unsigned), s));
+
         // queries -> bf16 [nq_pad, dim], zero padded, optionally normalised
         if ((rc = idx->ws_qbf16.ensure((size_t)nq_pad * idx->dim * 2)) != B2S_OK) return rc;
         {
@@ -153,18 +172,6 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
         }
         CUtensorMap qmap;
         if ((rc = tc_encode_rows(idx, &qmap, idx->ws_qbf16.p, (uint64_t)nq_pad, kTcQueriesPerCta)) != B2S_OK) return rc;
-
-        const size_t n_state = (size_t)num_lists * nq_pad;
-        if ((rc = idx->ws_lists.ensure(n_state * cap * sizeof(u64))) != B2S_OK) return rc;
-        if ((rc = idx->ws_counts.ensure(n_state * sizeof(int))) != B2S_OK) return rc;
-        if ((rc = idx->ws_thr.ensure(n_state * sizeof(u64))) != B2S_OK) return rc;
-        if ((rc = idx->ws_seed.ensure((size_t)nq_pad * sizeof(u64))) != B2S_OK) return rc;
-        if (sample_tiles > 0 && (rc = idx->ws_gmax.ensure((size_t)nq_pad * groups * sizeof(float))) != B2S_OK) return rc;
-        // shared-threshold state: [hist nq_pad*64 | gthr nq_pad] u32 (zeroed per call) + hcfg
-        const bool shared_thr = sample_tiles > 0 && idx->opt_tc_shared_thr != 0;
-        const size_t hist_words = (size_t)nq_pad * (kTcHistBins + 1);
-        if (shared_thr && (rc = idx->ws_hist.ensure(hist_words * sizeof(unsigned))) != B2S_OK) return rc;
-        if (shared_thr && (rc = idx->ws_hcfg.ensure((size_t)nq_pad * sizeof(uint2))) != B2S_OK) return rc;
 
         TcParams p;
         memset(&p, 0, sizeof(p));
@@ -192,18 +199,15 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
             pp.groups = groups;
             if (pair_mode) CUDA_TRY((tc_launch<true, true>(ctas, L.total + 1024, s, corpus_map, qmap, pp)));
             else CUDA_TRY((tc_launch<true, false>(ctas, L.total + 1024, s, corpus_map, qmap, pp)));
-            seed_select_kernel<<<(unsigned)nq_pad, kSeedThreads, 0, s>>>(
-                pp.gmax, groups, k, reinterpret_cast<u64*>(idx->ws_seed.p),
-                shared_thr ? reinterpret_cast<uint2*>(idx->ws_hcfg.p) : nullptr);
-            CUDA_TRY(cudaGetLastError());
+            const int sel_smem = (size_t)groups * 4 <= 40 * 1024 ? groups * 4 : 0;   // images staged in shared memory
+            CUDA_TRY(launch_pdl(seed_select_kernel, dim3((unsigned)nq_pad), dim3(kSeedThreads), (size_t)sel_smem, s,
+                                (const float*)pp.gmax, groups, k, reinterpret_cast<u64*>(idx->ws_seed.p),
+                                shared_thr ? reinterpret_cast<uint2*>(idx->ws_hcfg.p) : (uint2*)nullptr, sel_smem ? 1 : 0));
             idx->stats.kernel_launches += 2;
             p.seed_keys = reinterpret_cast<const u64*>(idx->ws_seed.p);
         }
 
-        CUDA_TRY(cudaMemsetAsync(idx->ws_counts.p, 0, n_state * sizeof(int), s));
-        CUDA_TRY(cudaMemsetAsync(idx->ws_thr.p, 0, n_state * sizeof(u64), s));
         if (shared_thr) {
-            CUDA_TRY(cudaMemsetAsync(idx->ws_hist.p, 0, hist_words * sizeof(unsigned), s));
             p.hcfg = reinterpret_cast<const uint2*>(idx->ws_hcfg.p);
             p.hist = reinterpret_cast<unsigned*>(idx->ws_hist.p);
             p.gthr = p.hist + (size_t)nq_pad * kTcHistBins;

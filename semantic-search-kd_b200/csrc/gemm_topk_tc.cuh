@@ -227,6 +227,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
     if constexpr (PAIR) ptx::cluster_sync_all();   // the peer's barriers exist before anything is signalled on them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    // programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on
+    // this kernel reads what its predecessors wrote (queries, seeds, zeroed list state)
+    grid_dep_wait();
 
     if (warp == 0) {
         // ================= TMA producer (both CTAs; bytes are counted on the leader's barriers) ====
@@ -476,6 +479,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
     }
 
     if (warp == 4 && lane == 0) *(volatile int*)s_cur_qb = kTcQbDone;
+    grid_dep_launch();   // the next kernel of the call (seed select / merge) may be scheduled
 
     // ---- teardown ---------------------------------------------------------------------------
     ptx::tc_fence_before();
@@ -494,14 +498,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
 constexpr int kSeedThreads = 256;
 __global__ void __launch_bounds__(kSeedThreads) seed_select_kernel(const float* __restrict__ gmax, int groups, int k,
                                                                    u64* __restrict__ seed_keys,
-                                                                   uint2* __restrict__ hcfg) {
+                                                                   uint2* __restrict__ hcfg, int in_smem) {
+    extern __shared__ uint32_t s_ord[];   // [groups] score images, when they fit (in_smem)
     __shared__ int hist[256];
     __shared__ uint32_t s_prefix;
     __shared__ int s_rem;
-    __shared__ uint32_t s_max;
+    __shared__ uint32_t s_red[2 * (kSeedThreads / 32)];
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
     const float* g = gmax + (size_t)q * groups;
+    grid_dep_launch();
+    grid_dep_wait();     // the pre-pass has written the group maxima
     if (groups < k) {
         if (tid == 0) {
             seed_keys[q] = 0ull;
@@ -509,26 +516,54 @@ __global__ void __launch_bounds__(kSeedThreads) seed_select_kernel(const float* 
         }
         return;
     }
-    if (tid == 0) s_max = 0u;
+    // one sweep over global memory (independent loads), min / max on the way
+    uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll 8
+    for (int i = tid; i < groups; i += kSeedThreads) {
+        const uint32_t o = score_to_ord(g[i]);
+        if (in_smem) s_ord[i] = o;
+        lo = o < lo ? o : lo;
+        hi = o > hi ? o : hi;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const uint32_t a = __shfl_xor_sync(0xffffffffu, lo, off), b = __shfl_xor_sync(0xffffffffu, hi, off);
+        lo = a < lo ? a : lo;
+        hi = b > hi ? b : hi;
+    }
+    if ((tid & 31) == 0) {
+        s_red[tid >> 5] = lo;
+        s_red[kSeedThreads / 32 + (tid >> 5)] = hi;
+    }
+    __syncthreads();
+    lo = s_red[0];
+    hi = s_red[kSeedThreads / 32];
+    for (int w = 1; w < kSeedThreads / 32; ++w) {
+        lo = s_red[w] < lo ? s_red[w] : lo;
+        hi = s_red[kSeedThreads / 32 + w] > hi ? s_red[kSeedThreads / 32 + w] : hi;
+    }
+    // MSB-first radix select of the k-th largest image, starting at the highest bit in which the
+    // candidates differ (the bits above it are common to all of them: nothing to histogram there)
+    int undecided = lo == hi ? 0 : 32 - __clz(lo ^ hi);      // low bits still to fix
     if (tid == 0) {
-        s_prefix = 0u;
+        s_prefix = undecided >= 32 ? 0u : (hi >> undecided) << undecided;
         s_rem = k;
     }
     __syncthreads();
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
+    while (undecided > 0) {
+        const int nb = undecided < 8 ? undecided : 8;
+        const int shift = undecided - nb;
         hist[tid] = 0;
         __syncthreads();
         const uint32_t prefix = s_prefix;
         for (int i = tid; i < groups; i += kSeedThreads) {
-            const uint32_t o = score_to_ord(g[i]);
-            if (pass == 0) atomicMax(&s_max, o);
-            const bool in = pass == 0 || (o >> (shift + 8)) == (prefix >> (shift + 8));
-            if (in) atomicAdd(&hist[(o >> shift) & 255u], 1);
+            const uint32_t o = in_smem ? s_ord[i] : score_to_ord(g[i]);
+            const bool in = undecided >= 32 || (o >> undecided) == (prefix >> undecided);
+            if (in) atomicAdd(&hist[(o >> shift) & ((1u << nb) - 1u)], 1);
         }
         __syncthreads();
         if (tid == 0) {
-            int rem = s_rem, b = 255;
+            int rem = s_rem, b = (1 << nb) - 1;
             for (; b > 0; --b) {
                 if (hist[b] >= rem) break;
                 rem -= hist[b];
@@ -537,17 +572,19 @@ __global__ void __launch_bounds__(kSeedThreads) seed_select_kernel(const float* 
             s_rem = rem;
         }
         __syncthreads();
+        undecided = shift;
     }
-    // s_prefix = ord of the k-th largest maximum T; every score >= T must pass: key > (ord << 32) - 1
+    // s_prefix = image of the k-th largest maximum T; every score >= T must pass: key > (T << 32) - 1
     if (tid == 0) {
-        seed_keys[q] = s_prefix ? (((u64)s_prefix << 32) - 1ull) : 0ull;
+        const uint32_t t = s_prefix;
+        seed_keys[q] = t ? (((u64)t << 32) - 1ull) : 0ull;
         if (hcfg) {
             // histogram geometry for the main pass: bins of 2^shift images from T up, the sample's best
             // score lands in bin <= 61; anything above goes to the last bin
-            const uint32_t range = s_max - s_prefix;
+            const uint32_t range = hi - t;
             uint32_t sh = 0;
             while ((range >> sh) > (uint32_t)(kTcHistBins - 3)) ++sh;
-            hcfg[q] = s_prefix ? make_uint2(s_prefix, sh) : make_uint2(0u, 0xffffffffu);
+            hcfg[q] = t ? make_uint2(t, sh) : make_uint2(0u, 0xffffffffu);
         }
     }
 }

@@ -60,6 +60,8 @@ __global__ void prep_queries_kernel(const void* __restrict__ in, int in_is_bf16,
                                     __nv_bfloat16* __restrict__ out_bf16) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // PDL: the kernel that follows (scan or tensor pre-pass) may be scheduled now; it waits for this grid
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (row >= nq_pad) return;
     if (row >= nq) {
         if (out_bf16)
