@@ -1217,7 +1217,8 @@ static int search_sharded_impl(b2s_index* idx, const void* queries, int q_dtype,
     a.flags_off = ex.flags_off;
     a.max_nq = ex.max_nq;
     a.nq = nq;
-    a.timeout_cycles = 4000000000ll;   // ~2 s: a missing peer must not hang the GPU
+    a.timeout_cycles = 60000000000ll;  // ~30 s of SM clock: ranks may be skewed by host work, but a missing
+                                       // peer must not hang the GPU for ever (the status word reports it)
     a.status = ex.status;
     a.out_scores = out_scores;
     a.out_ids = reinterpret_cast<long long*>(out_ids);
