@@ -496,7 +496,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=N_ROWS)
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 scan, 2 tensor")
-    ap.add_argument("--e2e-steps", type=int, default=500)
+    ap.add_argument("--e2e-steps", type=int, default=1000)
     ap.add_argument("--cpu-queries", type=int, default=48)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-hnsw", action="store_true")
