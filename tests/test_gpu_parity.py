@@ -548,3 +548,37 @@ def test_search_is_cuda_graph_capturable(pkg, oracle, nq, k):
         repo = oracle.compare_topk(out[0].cpu().numpy(), out[1].cpu().numpy(), Dr, Ir, X, Qn, tie_tol=TIE_TOL_BF16)
         assert repo["ok"], (rep, repo)
     idx.close()
+
+
+def test_search_handler_consumer_loop(pkg, oracle, tmp_path):
+    """The reference's /search handler consumes the index like this (/root/reference/src/serve/app.py:293-317):
+    `distances, indices = index_builder.search(query_emb, k=k)`, then for (dist, idx) in zip(distances[0],
+    indices[0]): skip `idx < 0`, `doc_ids[idx]`, `float(dist)`.  Run that loop on our index: after a
+    save()/load() round trip (app.py:427-433), with k > ntotal (the -1 padding the guard exists for)."""
+    X = unit_rows(50, 384, 171)
+    doc_ids = [f"doc_{i:03d}" for i in range(50)]
+    built = pkg.FAISSIndexBuilder(embedding_dim=384, index_type="HNSW", metric="cosine")
+    built.add(X, doc_ids)
+    built.save(tmp_path / "index")
+    index_builder = pkg.FAISSIndexBuilder(embedding_dim=384)          # app.py:427-429
+    index_builder.load(tmp_path / "index")                            # app.py:430-433
+    app_doc_ids = index_builder.doc_ids
+    query_emb = unit_rows(1, 384, 172)                                # encode_queries([...]) -> [1, 384] fp32
+    Dr, Ir = oracle.flat_ip_topk(X, query_emb, 50)
+    for k in (10, 50, 100):                                           # schemas.py:12 allows k up to 100
+        distances, indices = index_builder.search(query_emb, k=k)
+        results = []
+        for rank, (dist, idx) in enumerate(zip(distances[0], indices[0]), 1):
+            if idx < 0 or (app_doc_ids and idx >= len(app_doc_ids)):
+                continue
+            doc_id = app_doc_ids[idx] if app_doc_ids else f"doc_{idx}"
+            results.append({"doc_id": doc_id, "score": float(dist), "rank": rank})
+        assert len(results) == min(k, 50)
+        assert [r["rank"] for r in results] == list(range(1, len(results) + 1))
+        assert all(isinstance(r["score"], float) and -1.01 <= r["score"] <= 1.01 for r in results)
+        assert results[0]["doc_id"] == doc_ids[int(Ir[0, 0])]
+        assert sorted(r["score"] for r in results) == [r["score"] for r in results][::-1]
+        if k > 50:
+            assert list(indices[0][50:]) == [-1] * (k - 50)
+    built.close()
+    index_builder.close()
