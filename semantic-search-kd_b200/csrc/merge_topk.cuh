@@ -114,15 +114,29 @@ __device__ __forceinline__ int merge_lists_sorted(const MergeParams& p, const in
         // list can be cut at the first key under that floor: two dependent memory round trips in total,
         // no prefix sum, no gather of every candidate.
         u64* heads = reinterpret_cast<u64*>(hist);
-        for (int l = tid; l < kMergeMaxLists; l += NT) {
+        // the first four keys of every list come in with the counts, in ONE memory round trip: a list rarely
+        // has more than a few keys above the floor, so the walk below seldom touches memory again
+        constexpr int R = (kMergeMaxLists + NT - 1) / NT;
+        u64 pk[R][4];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int l = tid + r * NT;
             int c = 0;
-            u64 h = 0ull;
+            ulonglong2 a = make_ulonglong2(0ull, 0ull), b = a;
             if (l < L) {
                 c = __ldcg(p.counts + (size_t)l * p.nq_lists + q);
-                h = __ldcg(p.lists + ((size_t)l * p.nq_lists + q) * p.cap);   // garbage when the list is empty
+                const ulonglong2* lp2 = reinterpret_cast<const ulonglong2*>(p.lists + ((size_t)l * p.nq_lists + q) * p.cap);
+                a = __ldcg(lp2);       // (garbage beyond the list's count, masked below; cap >= 64 keys)
+                b = __ldcg(lp2 + 1);
             }
-            offs[l] = c;
-            heads[l] = c > 0 ? h : 0ull;
+            pk[r][0] = c > 0 ? a.x : 0ull;
+            pk[r][1] = c > 1 ? a.y : 0ull;
+            pk[r][2] = c > 2 ? b.x : 0ull;
+            pk[r][3] = c > 3 ? b.y : 0ull;
+            if (l < kMergeMaxLists) {
+                offs[l] = c;
+                heads[l] = pk[r][0];
+            }
         }
         if (tid == 0) {
             s_floor = 0ull;
@@ -146,14 +160,26 @@ __device__ __forceinline__ int merge_lists_sorted(const MergeParams& p, const in
         }
         __syncthreads();
         const u64 floor_key = s_floor;
-        for (int l = tid; l < L; l += NT) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int l = tid + r * NT;
+            if (l >= L) continue;
             const int c = offs[l];
             const u64* lp = p.lists + ((size_t)l * p.nq_lists + q) * p.cap;
-            u64 key = heads[l];
-            for (int i = 0; i < c && key >= floor_key; ) {
-                const int pos = atomicAdd(&s_fill, 1);
-                if (pos < kMergeFastCap) sel[pos] = key;
-                if (++i < c) key = __ldcg(lp + i);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i < c && pk[r][i] >= floor_key && (i == 0 || pk[r][i - 1] >= floor_key)) {
+                    const int pos = atomicAdd(&s_fill, 1);
+                    if (pos < kMergeFastCap) sel[pos] = pk[r][i];
+                }
+            }
+            if (c > 4 && pk[r][3] >= floor_key) {   // rare: more than four keys of one list above the floor
+                for (int i = 4; i < c; ++i) {
+                    const u64 key = __ldcg(lp + i);
+                    if (key < floor_key) break;
+                    const int pos = atomicAdd(&s_fill, 1);
+                    if (pos < kMergeFastCap) sel[pos] = key;
+                }
             }
         }
         __syncthreads();
