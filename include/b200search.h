@@ -107,6 +107,13 @@ B2S_API int b2s_set_id_offset(b2s_index* idx, int64_t offset);
  *   "tc_min_nq"   smallest query batch that takes the tensor path (default 3)
  *   "tc_sample_div"  threshold pre-pass samples 1/div of the corpus tiles (0 = chosen by k)
  *   "tc_chunk_tiles" tiles per work item when several query blocks share the corpus
+ *   "tc_shared_thr"  1 (default): thresholds tighten GPU-wide through a per-query survivor histogram
+ *   "tc_thr_period_ns" refresh period of the histogram's bound-updater warp (default 10000)
+ *   "tc_single_cta"  1 (default): batches of <= 128 queries use single-CTA MMAs (M = 128)
+ *   "fused_tail"  1 (default): the scan kernel's last CTA merges (and exchanges) in the same launch
+ *   "exchange_ll" 1 (default): fused exchange uses sequence-tagged 8-byte words (no fence, no flag)
+ *   "host_inline" 1 (default): host-buffer calls of 1-2 queries pass the query in the kernel
+ *                 parameters and receive the answer in mapped pinned memory (no copy operations)
  */
 B2S_API int b2s_set_option(b2s_index* idx, const char* name, int64_t value);
 B2S_API int64_t b2s_get_option(const b2s_index* idx, const char* name);
