@@ -582,3 +582,63 @@ def test_search_handler_consumer_loop(pkg, oracle, tmp_path):
             assert list(indices[0][50:]) == [-1] * (k - 50)
     built.close()
     index_builder.close()
+
+
+def test_packed_merge_single_gpu(pkg, oracle):
+    """b2s_merge_packed_device (the NCCL all-gather variant's K4) on one GPU: G shard results written into
+    the packed [ids | scores] blocks exactly as ShardedFlatIPIndex lays them out, merged, compared."""
+    import ctypes
+    import torch
+    from semantic_search_kd_b200.sharded import packed_bytes, shard_range
+    L = pkg._lib.lib()
+    dev = torch.device("cuda", 0)
+    n, nq, k, G = 30011, 9, 20, 4
+    X, Q = unit_rows(n, 384, 181), unit_rows(nq, 384, 182)
+    X[20000] = X[3]                                              # a tie across shards
+    Q[0] = X[3]
+    q = torch.from_numpy(Q).to(dev)
+    per = packed_bytes(nq, k)
+    assert per == L.b2s_packed_bytes(nq, k)
+    gathered = torch.zeros((G, per), dtype=torch.uint8, device=dev)
+    shards = []
+    for r in range(G):
+        lo, hi = shard_range(n, G, r)
+        sh = build(pkg, X[lo:hi])
+        sh.set_id_offset(lo)
+        ids = gathered[r][: nq * k * 8].view(torch.int64).view(nq, k)
+        scores = gathered[r][nq * k * 8: nq * k * 12].view(torch.float32).view(nq, k)
+        sh.search_device(q, k, out=(scores, ids))
+        shards.append(sh)
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    rc = L.b2s_merge_packed_device(0, ctypes.c_void_p(gathered.data_ptr()), G, nq, k, ctypes.c_void_p(out_s.data_ptr()),
+                                   ctypes.c_void_p(out_i.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    assert rc == 0, pkg._lib.last_error()
+    torch.cuda.synchronize()
+    whole = build(pkg, X)
+    D, I = whole.search(Q, k)
+    assert np.array_equal(out_i.cpu().numpy(), I) and np.allclose(out_s.cpu().numpy(), D, atol=1e-6)
+    assert list(I[0][:2]) == [3, 20000]
+    for sh in shards + [whole]:
+        sh.close()
+
+
+def test_small_api_surface(pkg):
+    import ctypes
+    L = pkg._lib.lib()
+    idx = build(pkg, unit_rows(100, 384, 1))
+    h = idx._h
+    assert L.b2s_dim(h) == 384 and L.b2s_ntotal(h) == 100 and L.b2s_device_count() >= 1
+    assert L.b2s_get_option(h, b"path") == 0 and L.b2s_get_option(h, b"num_sms") > 100
+    assert L.b2s_get_option(h, b"no_such_option") == -1
+    assert L.b2s_set_option(h, b"no_such_option", 1) == pkg._lib.B2S_ERR_INVALID
+    assert L.b2s_set_option(h, b"path", 7) == pkg._lib.B2S_ERR_INVALID
+    assert L.b2s_reserve(h, 5000) == 0 and L.b2s_ntotal(h) == 100
+    D0, I0 = idx.search(unit_rows(2, 384, 2), 5)
+    assert L.b2s_reset(h) == 0 and L.b2s_ntotal(h) == 0
+    D, I = idx.search(unit_rows(2, 384, 2), 5)
+    assert (I == -1).all()                                      # empty index: padding only
+    idx.add(unit_rows(100, 384, 1))
+    D1, I1 = idx.search(unit_rows(2, 384, 2), 5)
+    assert np.array_equal(I0, I1) and np.array_equal(D0, D1)
+    idx.close()
