@@ -465,7 +465,7 @@ int search_core(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, in
     idx->stats.path = path;
     const bool normalize = idx->metric == B2S_METRIC_COSINE;
     // Threshold seeding: on the scan path a pre-pass over every 64th unit pays for itself once the
-    // per-CTA cold start matters (k >= 32 on a large shard); the tensor path always bounds the
+    // per-CTA cold start matters (nq * k > 128 on a large shard); the tensor path always bounds the
     // k-th best score from a row sample first (its lists are private to one thread).
     // (measured with the fused merge tail, 8.8M rows: one unseeded launch wins up to nq * k = 128 --
     //  k = 100 at batch 1: 0.984 ms vs 0.993 ms seeded; k = 200: 1.037 vs 1.010)
