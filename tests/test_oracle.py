@@ -133,3 +133,17 @@ def test_hnsw_restatement_recall_small(oracle):
     _, Ih = h.search(Q, 10, ef_search=64)
     _, If = oracle.flat_ip_topk(X, Q, 10)
     assert oracle.recall_at_k(Ih, If) > 0.9
+
+
+def test_hnsw_restatement_recall_grows_with_ef_search(oracle):
+    """On isotropic 384-d data (the worst case for a graph index, and what BASELINE config 0 prescribes)
+    the restated HNSW's recall@10 is low at efSearch=64 but rises monotonically to ~1 with efSearch:
+    the graph is sound, the data is hard."""
+    X, Q = oracle.gen_unit_rows(6000, 384, 0), oracle.gen_unit_rows(100, 384, 1)
+    h = oracle.HnswRef(X, M=32, ef_construction=200, nthreads=4)
+    _, If = oracle.flat_ip_topk(X, Q, 10, acc="f32")
+    rec = []
+    for ef in (16, 64, 256, 2048):
+        _, Ih = h.search(Q, 10, ef_search=ef, nthreads=4)
+        rec.append(oracle.recall_at_k(Ih, If))
+    assert rec == sorted(rec) and rec[-1] >= 0.99 and rec[0] < rec[-1], rec
