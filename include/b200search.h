@@ -10,6 +10,9 @@
  * plain pointers and sizes, never throw, never abort; they return B2S_OK (0)
  * or a negative B2S_ERR_* code with a thread-local message in b2s_last_error().
  *
+ * Inputs are expected to be finite.  A NaN score never passes a threshold test, so rows (or queries)
+ * containing NaN simply do not appear in results; nothing crashes.
+ *
  * Threading: one in-flight call per index handle (calls on the same handle are
  * serialised by an internal mutex), matching the reference's single-worker,
  * event-loop-thread use of .search (src/serve/app.py:258,293; src/config.py:213).

@@ -642,3 +642,24 @@ def test_small_api_surface(pkg):
     D1, I1 = idx.search(unit_rows(2, 384, 2), 5)
     assert np.array_equal(I0, I1) and np.array_equal(D0, D1)
     idx.close()
+
+
+def test_nan_rows_and_queries_do_not_crash(pkg, oracle):
+    """A NaN score fails every threshold test: NaN rows never appear, a NaN query returns only padding."""
+    X, Q = unit_rows(5000, 384, 191), unit_rows(6, 384, 192)
+    Xn = X.copy()
+    Xn[17, 5] = np.nan
+    Xn[4000] = np.nan
+    for path in (1, 2):
+        idx = build(pkg, Xn, path=path)
+        D, I = idx.search(Q, 10)
+        assert not np.isin(I, [17, 4000]).any() and np.isfinite(D).all()
+        Xc = X.copy()
+        Xc[[17, 4000]] = 0.0                              # the oracle sees them as rows that cannot win
+        Dr, Ir = oracle.flat_ip_topk(Xc, Q, 10)
+        assert oracle.compare_topk(D, I, Dr, Ir, Xc, Q, tie_tol=TIE_TOL_BF16)["ok"]
+        qn = Q.copy()
+        qn[0, 0] = np.nan
+        D, I = idx.search(qn, 10)
+        assert (I[0] == -1).all() and (I[1:] >= 0).all()
+        idx.close()
