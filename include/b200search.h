@@ -13,9 +13,14 @@
  * Inputs are expected to be finite.  A NaN score never passes a threshold test, so rows (or queries)
  * containing NaN simply do not appear in results; nothing crashes.
  *
- * Threading: one in-flight call per index handle (calls on the same handle are
- * serialised by an internal mutex), matching the reference's single-worker,
- * event-loop-thread use of .search (src/serve/app.py:258,293; src/config.py:213).
+ * Threading and streams: one in-flight call per index handle, matching the reference's
+ * single-worker, event-loop-thread use of .search (src/serve/app.py:258,293;
+ * src/config.py:213).  Host-side enqueueing is serialised by an internal mutex.  The handle's
+ * workspaces are shared by all of its searches: a device-API call enqueued on ANOTHER stream
+ * than the handle's previous search first waits (event) for everything enqueued on that
+ * previous stream, so searches of one handle never overlap on the device whatever streams they
+ * are issued on; host-API calls run on a private stream under the same rule.  (A search
+ * captured into a CUDA graph is exempt: whoever replays the graph orders it.)
  */
 #ifndef B200SEARCH_H
 #define B200SEARCH_H
@@ -46,6 +51,17 @@ enum {
 enum { B2S_METRIC_INNER_PRODUCT = 0, B2S_METRIC_COSINE = 1 };
 enum { B2S_DTYPE_F32 = 0, B2S_DTYPE_BF16 = 1 };
 enum { B2S_PATH_AUTO = 0, B2S_PATH_SCAN = 1, B2S_PATH_TENSOR = 2 };
+
+/*
+ * Flags of the device-buffer searches.
+ * B2S_SEARCH_STABLE_QUERIES: the caller guarantees that the query buffer was completely written
+ *   before the PREVIOUS operation on cuda_stream was enqueued (a pre-encoded query set, a ring of
+ *   query slots filled ahead, ...).  The batch-1/2 scan kernel may then start streaming the corpus
+ *   while the previous search's tail (candidate merge, cross-GPU exchange) is still running
+ *   (programmatic dependent launch with a deferred wait).  Without the flag the kernel only
+ *   prefetches immutable corpus rows into L2 before it waits.  Results are identical either way.
+ */
+enum { B2S_SEARCH_STABLE_QUERIES = 1u };
 
 /* Per-call counters of the last search on a handle (b2s_last_stats). */
 typedef struct b2s_stats {
@@ -85,6 +101,13 @@ B2S_API int b2s_reserve(b2s_index* idx, int64_t n_rows);
  */
 B2S_API int b2s_add_f32(b2s_index* idx, const float* rows, int64_t n, int is_device);
 B2S_API int b2s_add_bf16(b2s_index* idx, const void* rows, int64_t n, int is_device);
+/*
+ * Append rows VERBATIM (dtype B2S_DTYPE_F32 -> rounded to bf16, B2S_DTYPE_BF16 -> copied bit for
+ * bit), without the cosine metric's normalisation: the rows are what the index is to hold.  This
+ * is what FAISSIndexBuilder.load (src/serve/app.py:430-433) needs: rows saved by save() come back
+ * bit-identical however often an index is saved and loaded.
+ */
+B2S_API int b2s_add_prepared(b2s_index* idx, const void* rows, int dtype, int64_t n, int is_device);
 
 /* index.ntotal (scripts/build_faiss_index.py:72). */
 B2S_API int64_t b2s_ntotal(const b2s_index* idx);
@@ -103,10 +126,17 @@ B2S_API int b2s_set_id_offset(b2s_index* idx, int64_t offset);
  *   "rescore_pad" extra candidates re-scored in fp32 when keep_f32 is on
  *   "timing"      N > 0: every N-th search records CUDA events around its dominant kernel and the
  *                 whole call (b2s_last_stats / b2s_read_timings); 0 = off
- *   "pdl"         0 off | 1 (default) programmatic dependent launch hides the launch latency
- *                 between the scan and merge kernels | 2 additionally lets the scan of call i+1
- *                 overlap the merge of call i; valid only if the query buffer of a call is not
- *                 written by the kernel enqueued immediately before it on the same stream
+ *   "pdl"         0 off | 1 (default) programmatic dependent launch between this handle's kernels
+ *                 | 2 treat every device call as if B2S_SEARCH_STABLE_QUERIES were set (per handle)
+ *   "pdl_early"   1 (default): the scan kernel triggers its dependent launch at its start, so the next search's
+ *                 CTAs take over SM slots as this one's retire (no launch gap); 0 = after the scan
+ *   "prefetch_iters" scan kernel: iterations per warp prefetched into L2 before the PDL wait (default 6)
+ *   "dynamic_tail"   scan kernel: units per CTA dealt by ticket at the end of the scan (default 3, 0 = static)
+ *   "cascade"     1 (default): k <= 16 on large shards keeps the running global top-k in k sorted
+ *                 device slots (lock-free atomicMax insertion) instead of per-CTA lists + merge
+ *   "phase_a"     cascade: iterations against the CTA-local lists before the slots take over (0 = auto)
+ *   "trace"       1: the scan kernel stamps %globaltimer at its phase boundaries (b2s_read_trace)
+ *   "exchange_timeout_ms" bound of a sharded search's wait for a peer rank (default 10000)
  *   "tc_min_nq"   smallest query batch that takes the tensor path (default 3)
  *   "tc_sample_div"  threshold pre-pass samples 1/div of the corpus tiles (0 = chosen by k)
  *   "tc_chunk_tiles" tiles per work item when several query blocks share the corpus
@@ -134,12 +164,12 @@ B2S_API int b2s_search(b2s_index* idx, const float* queries, int64_t nq, int k, 
 /*
  * Same search with DEVICE buffers on the index's device, enqueued on
  * cuda_stream (a cudaStream_t; NULL = the legacy default stream).  q_dtype is
- * B2S_DTYPE_F32 or B2S_DTYPE_BF16.  Returns after enqueueing; no host sync.
+ * B2S_DTYPE_F32 or B2S_DTYPE_BF16; flags = 0 or B2S_SEARCH_*.  Returns after enqueueing; no host sync.
  * For a row-sharded corpus this is the per-shard "local top-k" whose outputs
  * feed the all-gather and b2s_merge_device.
  */
 B2S_API int b2s_search_device(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, int k,
-                              float* out_scores, int64_t* out_ids, void* cuda_stream);
+                              float* out_scores, int64_t* out_ids, void* cuda_stream, unsigned flags);
 
 /*
  * Merge G sorted candidate lists per query into the global top-k (after the
@@ -216,7 +246,13 @@ B2S_API int b2s_ance_filter_device(int device, const float* cand_scores, const i
  *                         calls with the same (nq, k).  phase 0 = whole call; phase 1 = local
  *                         search + push only and phase 2 = wait + merge only (lets a test run
  *                         several emulated ranks one after the other on a single GPU).
- *   b2s_exchange_status   0, or the sequence number of a call whose wait timed out (synchronises)
+ *   b2s_exchange_status   0, or the sequence number of a call whose wait timed out (synchronises).
+ *                         A timeout is never silent: the host-buffer call that hit it returns
+ *                         B2S_ERR_CUDA, and so does every later sharded call on the handle.
+ * world * k is not limited by the merge buffer: above 4096 candidates per query the ranks' sorted
+ * blocks are merged by binary search (8 ranks x k = 2048 works).  k itself is <= 2048 everywhere
+ * (the reference's serving schema allows <= 100 / 200, src/serve/schemas.py:12-16; its
+ * SearchConfig.max_top_k = 10000, src/config.py:227, is refused with B2S_ERR_UNSUPPORTED).
  */
 B2S_API int b2s_exchange_create(b2s_index* idx, int world, int rank, int64_t slot_bytes, int max_nq,
                                 void* ipc_handle_out);
@@ -224,7 +260,8 @@ B2S_API void* b2s_exchange_local(const b2s_index* idx);
 B2S_API int b2s_exchange_connect(b2s_index* idx, const void* handles, int raw_pointers);
 B2S_API int b2s_exchange_status(b2s_index* idx);
 B2S_API int b2s_search_sharded_device(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, int k,
-                                      float* out_scores, int64_t* out_ids, void* cuda_stream, int phase);
+                                      float* out_scores, int64_t* out_ids, void* cuda_stream, int phase,
+                                      unsigned flags);
 /* HOST-buffer variant of the whole sharded call (phase 0): H2D + exchange + D2H inside; every rank
  * gets the global top-k.  This is what ShardedFlatIPIndex.search(np.ndarray, k) calls. */
 B2S_API int b2s_search_sharded(b2s_index* idx, const float* queries, int64_t nq, int k, float* out_scores,
@@ -249,6 +286,16 @@ B2S_API int b2s_last_stats(const b2s_index* idx, b2s_stats* out);
  * last (up to max_n, ring of 4096) calls' device times in ms, oldest first.  Returns the count.
  */
 B2S_API int b2s_read_timings(const b2s_index* idx, float* dominant_ms, float* total_ms, int max_n);
+
+/*
+ * With option "trace" = 1 the scan kernel of a batch-1/2 search stamps the GPU-wide nanosecond timer:
+ * word 1 = the last CTA to finish holds the ticket (every CTA's scan is done), 2 = the local top-k is
+ * ready, 3 = pushed to the peer ranks, 4 = every peer's candidates have arrived, 5 = outputs written,
+ * word 0 = G (CTAs); then six arrays of 512 words, entry b = CTA b: start (after the dependency
+ * wait), end of scan, cascade transition begin / end, end of the static part, SM id.
+ * Synchronises the device and copies up to max_words words (16 + 6 * 512 for all); returns the count.
+ */
+B2S_API int b2s_read_trace(b2s_index* idx, uint64_t* out, int max_words);
 
 #ifdef __cplusplus
 }

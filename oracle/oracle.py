@@ -153,6 +153,16 @@ def ance_filter_ref(cand_ids, cand_scores, pos_scores, margin: float, top_k: int
     return [d for d, _ in adv[:top_k]]
 
 
+def maxsim_ref(chunk_scores) -> dict:
+    """MaxSim, restated (``src/utils/chunk.py:123-148``): ``[("{doc}_{chunk_idx}", score), ...]`` ->
+    ``{doc: best chunk score}``; an id without ``_`` is its own document."""
+    best: dict = {}
+    for cid, sc in chunk_scores:
+        doc = cid.rsplit("_", 1)[0] if "_" in cid else cid
+        best[doc] = max(sc, best[doc]) if doc in best else sc
+    return best
+
+
 # ---------------------------------------------------------------------------
 # C oracle (large cases, streaming)
 # ---------------------------------------------------------------------------
@@ -260,12 +270,16 @@ def compare_topk(D_test: np.ndarray, I_test: np.ndarray, D_ref: np.ndarray, I_re
     Ids must equal the oracle's.  After removing common ids, an id only we
     returned (and symmetrically an id only the oracle returned) is accepted iff
     its fp32 score (recomputed here in fp64 from X, Q) is within ``tie_tol`` of
-    the oracle's k-th score.  Returns counters; ``ok`` is the verdict.
+    the oracle's k-th score.  ORDER is checked as well, position by position: where our id at
+    rank j differs from the oracle's, its true score must be within ``2 * tie_tol`` of the oracle's
+    j-th score (a storage error of eps per row moves the j-th order statistic by at most eps and
+    the row's own score by another eps), and the true scores of our list may never increase by
+    more than ``2 * tie_tol`` from one rank to the next.  Returns counters; ``ok`` is the verdict.
     """
     X = _f32(X)
     Q = _f32(Q)
     nq, k = I_ref.shape
-    exact_order = set_match = swaps = bad = 0
+    exact_order = set_match = swaps = bad = order_bad = 0
     max_err = 0.0
     bad_examples = []
     for i in range(nq):
@@ -283,9 +297,15 @@ def compare_topk(D_test: np.ndarray, I_test: np.ndarray, D_ref: np.ndarray, I_re
             continue
         if valid.any():
             kth = float(D_ref[i][valid][-1])
+            prev = None
             for j in np.nonzero(a >= 0)[0]:
                 s = float(np.dot(Q[i].astype(np.float64), X[int(a[j])].astype(np.float64)))
                 max_err = max(max_err, abs(s - float(D_test[i, j])))
+                if (a[j] != b[j] and abs(s - float(D_ref[i, j])) > 2 * tie_tol) or \
+                        (prev is not None and s > prev + 2 * tie_tol):
+                    order_bad += 1
+                    bad_examples.append((i, "order", int(j), int(a[j]), s, float(D_ref[i, j])))
+                prev = s
             for x in (sa - sb) | (sb - sa):
                 s = float(np.dot(Q[i].astype(np.float64), X[x].astype(np.float64)))
                 if abs(s - kth) <= tie_tol:
@@ -294,5 +314,5 @@ def compare_topk(D_test: np.ndarray, I_test: np.ndarray, D_ref: np.ndarray, I_re
                     bad += 1
                     bad_examples.append((i, x, s, kth))
     return {"nq": nq, "k": k, "exact_order": exact_order, "set_match": set_match,
-            "tie_swaps": swaps, "violations": bad, "max_abs_score_err": max_err,
-            "ok": bad == 0, "examples": bad_examples[:5]}
+            "tie_swaps": swaps, "violations": bad, "order_violations": order_bad, "max_abs_score_err": max_err,
+            "ok": bad == 0 and order_bad == 0, "examples": bad_examples[:5]}

@@ -8,7 +8,7 @@ from . import _lib  # noqa: F401
 from .errors import (DeviceError, IndexBuildError, IndexNotBuiltError, IndexNotFoundError,  # noqa: F401
                      SearchIndexError)
 from .index import FAISSIndexBuilder, FlatIPIndex  # noqa: F401
-from .mining import ANCEMiner, maxsim_aggregation, maxsim_topk, retrieve_topk, similarity  # noqa: F401
+from .mining import ANCEMiner, maxsim_topk, retrieve_topk, similarity  # noqa: F401
 
-__all__ = ["FlatIPIndex", "FAISSIndexBuilder", "ANCEMiner", "similarity", "retrieve_topk", "maxsim_aggregation", "maxsim_topk", "IndexNotFoundError", "IndexNotBuiltError",
+__all__ = ["FlatIPIndex", "FAISSIndexBuilder", "ANCEMiner", "similarity", "retrieve_topk", "maxsim_topk", "IndexNotFoundError", "IndexNotBuiltError",
            "IndexBuildError", "DeviceError", "SearchIndexError"]

@@ -30,6 +30,7 @@ METRIC_COSINE = 1
 DTYPE_F32 = 0
 DTYPE_BF16 = 1
 PATH_AUTO, PATH_SCAN, PATH_TENSOR = 0, 1, 2
+SEARCH_STABLE_QUERIES = 1
 
 # every symbol include/b200search.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -39,7 +40,7 @@ EXPORTS = [
     "b2s_similarity", "b2s_read_rows_f32", "b2s_rows_device", "b2s_last_stats", "b2s_read_timings",
     "b2s_packed_bytes", "b2s_merge_packed_device", "b2s_score_rows_device", "b2s_ance_filter_device",
     "b2s_exchange_create", "b2s_exchange_local", "b2s_exchange_connect", "b2s_exchange_status",
-    "b2s_search_sharded_device", "b2s_search_sharded", "b2s_maxsim_device",
+    "b2s_search_sharded_device", "b2s_search_sharded", "b2s_maxsim_device", "b2s_add_prepared", "b2s_read_trace",
 ]
 
 
@@ -81,7 +82,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if res.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
         if verbose:
-            print(res.stderr)
+            import re
+            for m in re.finditer(r"Compiling entry function '(\w+)'.*?Used (\d+) registers[^\n]*", res.stderr, re.S):
+                print(f"{m.group(2):>4} regs  {m.group(1)[:90]}")
+            for ln in res.stderr.splitlines():
+                if "spill" in ln and "0 bytes spill stores, 0 bytes spill loads" not in ln:
+                    print(ln)
     return _SO
 
 
@@ -118,7 +124,7 @@ def lib() -> ctypes.CDLL:
     L.b2s_get_option.argtypes = [vp, ctypes.c_char_p]
     L.b2s_get_option.restype = i64
     L.b2s_search.argtypes = [vp, vp, i64, i32, vp, vp]
-    L.b2s_search_device.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp]
+    L.b2s_search_device.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp, ctypes.c_uint]
     L.b2s_merge_device.argtypes = [i32, vp, vp, i32, i64, i32, vp, vp, vp]
     L.b2s_similarity.argtypes = [i32, vp, i64, vp, i64, i32, vp]
     L.b2s_read_rows_f32.argtypes = [vp, i64, i64, vp]
@@ -143,12 +149,16 @@ def lib() -> ctypes.CDLL:
     L.b2s_exchange_connect.restype = i32
     L.b2s_exchange_status.argtypes = [vp]
     L.b2s_exchange_status.restype = i32
-    L.b2s_search_sharded_device.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp, i32]
+    L.b2s_search_sharded_device.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp, i32, ctypes.c_uint]
     L.b2s_search_sharded_device.restype = i32
     L.b2s_search_sharded.argtypes = [vp, vp, i64, i32, vp, vp]
     L.b2s_search_sharded.restype = i32
     L.b2s_maxsim_device.argtypes = [i32, vp, vp, i64, i32, vp, i64, i32, vp, vp, vp, vp]
     L.b2s_maxsim_device.restype = i32
+    L.b2s_add_prepared.argtypes = [vp, vp, i32, i64, i32]
+    L.b2s_add_prepared.restype = i32
+    L.b2s_read_trace.argtypes = [vp, vp, i32]
+    L.b2s_read_trace.restype = i32
     for name in ("b2s_create", "b2s_destroy", "b2s_reserve", "b2s_add_f32", "b2s_add_bf16", "b2s_dim",
                  "b2s_reset", "b2s_set_id_offset", "b2s_set_option", "b2s_search", "b2s_search_device",
                  "b2s_merge_device", "b2s_similarity", "b2s_read_rows_f32", "b2s_last_stats"):

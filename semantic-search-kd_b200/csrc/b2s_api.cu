@@ -8,6 +8,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <float.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -138,13 +139,35 @@ struct b2s_index {
         long long slot_stride = 0, flags_off = 0, ll_off = 0, ll_entries = 0;
         unsigned char** peers_dev = nullptr;   // device array [world]
         std::vector<void*> opened;             // cudaIpcOpenMemHandle'd peer mappings
-        unsigned* status = nullptr;            // device word
+        unsigned* status = nullptr;            // mapped pinned host word: the kernels store the sequence number of
+                                               // a call whose wait timed out, the host reads it without a copy
         unsigned seq = 0;
         bool connected = false;
+        int max_fused_nq = 0;                  // CTAs of the fused merge+exchange kernel that are co-resident
+        long long timeout_ms = 10000;
     } ex;
     const ExchangeArgs* ex_call = nullptr;
     int ex_fused = 0;
-    unsigned* done_counter = nullptr;   // device word for the scan kernel's fused merge tail
+    // device control block of the scan kernel: done ticket, dynamic-tail work counters, the cascade select's
+    // global slots [kScanMaxNQ][kCascadeMaxK] u64 -- all zero between launches
+    unsigned* done_counter = nullptr;
+    unsigned* work_counter = nullptr;
+    u64* gslots = nullptr;
+    unsigned long long* trace_buf = nullptr;   // option "trace": globaltimer stamps of the last scan launch
+    int opt_trace = 0;
+    int opt_prefetch_iters = 6;         // iterations per warp prefetched into L2 before the PDL wait (0 = off)
+    int opt_dynamic_tail = 3;           // units per CTA dealt dynamically at the end of the scan (0 = all static)
+    int opt_cascade = 1;                // k <= 16 on large shards: global sorted slots instead of per-CTA lists
+    int opt_phase_a = 0;                // cascade: iterations against the local lists first (0 = auto)
+    int opt_phase_a_stagger = 64;       // cascade: CTA b switches to the global slots b % this iterations later
+    int opt_transition_mode = 1;        // cascade: see ScanParams::transition_mode
+    int opt_pdl_early = 1;              // scan kernel triggers its dependent launch at its start (see ScanParams::early_trigger)
+    int opt_peek_every = 0;             // cascade: iterations between re-reads of the slots' k-th key (0 = only after inserts)
+    unsigned call_flags = 0;            // B2S_SEARCH_* of the call in flight
+    // stream of the previous search: a call on another stream first waits for everything enqueued there
+    cudaStream_t last_stream = nullptr;
+    bool last_stream_valid = false;
+    cudaEvent_t xs_event = nullptr;
     const float* host_q = nullptr;      // host-buffer call in flight: its queries may ride in the kernel parameters
     int opt_fused_tail = 1;
     int opt_host_inline = 1;            // host-buffer calls of 1-2 queries: query in the kernel parameters, answer
@@ -204,12 +227,10 @@ int grow_rows(b2s_index* idx, int64_t need_rows) {
 // K1 dispatch
 // ---------------------------------------------------------------------------------------------
 
-bool g_pdl_enabled = true;   // process-wide switch ("pdl" option 0 turns it off for debugging)
-
 // Launch with programmatic dependent launch allowed: the kernel may begin while its predecessor in
 // the stream is still running and synchronises on it with grid_dep_wait() (select.cuh).
 template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid;
@@ -218,14 +239,16 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = g_pdl_enabled ? 1 : 0;
+    at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = at;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
+std::mutex g_attr_mu;   // guards the once-per-device function attribute flags below
+
 template <int CPL, int NQ, int U>
-int launch_scan_t(const ScanParams& p, int grid, cudaStream_t s) {
+int launch_scan_t(const ScanParams& p, int grid, cudaStream_t s, bool pdl) {
     const size_t smem = (size_t)NQ * p.cap * sizeof(u64);
     auto kern = scan_topk_kernel<CPL, NQ, U>;
     // dynamic candidate lists sit next to ~44 KB of static shared memory (the fused merge tail): opt in
@@ -233,11 +256,14 @@ int launch_scan_t(const ScanParams& p, int grid, cudaStream_t s) {
     static bool attr_set[64] = {};   // per device: function attributes belong to the device's context
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ * 4096 * (int)sizeof(u64)));
-        attr_set[dev] = true;
+    if (dev >= 0 && dev < 64) {
+        std::lock_guard<std::mutex> g(g_attr_mu);
+        if (!attr_set[dev]) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ * 4096 * (int)sizeof(u64)));
+            attr_set[dev] = true;
+        }
     }
-    CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(kScanThreads), smem, s, p));
+    CUDA_TRY(launch_pdl(pdl, kern, dim3(grid), dim3(kScanThreads), smem, s, p));
     return B2S_OK;
 }
 
@@ -251,10 +277,10 @@ int scan_max_nq(int dim) {
 
 int scan_rows_per_iter(int dim) { return (dim / 128 <= 3) ? 8 : 4; }
 
-int launch_scan(int dim, int nq_group, const ScanParams& p, int grid, cudaStream_t s) {
+int launch_scan(int dim, int nq_group, const ScanParams& p, int grid, cudaStream_t s, bool pdl) {
     const int cpl = dim / 128;
 #define B2S_SCAN_CASE(C, Q, UU) \
-    if (cpl == C && nq_group == Q) return launch_scan_t<C, Q, UU>(p, grid, s);
+    if (cpl == C && nq_group == Q) return launch_scan_t<C, Q, UU>(p, grid, s, pdl);
     B2S_SCAN_CASE(1, 1, 4) B2S_SCAN_CASE(1, 2, 4) B2S_SCAN_CASE(1, 4, 4)
     B2S_SCAN_CASE(2, 1, 4) B2S_SCAN_CASE(2, 2, 4) B2S_SCAN_CASE(2, 4, 4)
     B2S_SCAN_CASE(3, 1, 4) B2S_SCAN_CASE(3, 2, 4) B2S_SCAN_CASE(3, 4, 4)
@@ -277,10 +303,11 @@ int launch_merge(const b2s_index* idx, const MergeParams& mp, int nq, int q_offs
     if (idx->ex_call != nullptr && mp.out_kth_key == nullptr) {
         ExchangeArgs ex = *idx->ex_call;
         ex.q_offset = q_offset;
-        if (idx->ex_fused) CUDA_TRY(launch_pdl(merge_exchange_kernel<true>, dim3(nq), dim3(kMergeThreads), 0, s, mp, ex));
-        else CUDA_TRY(launch_pdl(merge_exchange_kernel<false>, dim3(nq), dim3(kMergeThreads), 0, s, mp, ex));
+        const bool pdl = idx->opt_pdl != 0;
+        if (idx->ex_fused) CUDA_TRY(launch_pdl(pdl, merge_exchange_kernel<true>, dim3(nq), dim3(kMergeThreads), 0, s, mp, ex));
+        else CUDA_TRY(launch_pdl(pdl, merge_exchange_kernel<false>, dim3(nq), dim3(kMergeThreads), 0, s, mp, ex));
     } else {
-        CUDA_TRY(launch_pdl(merge_topk_kernel, dim3(nq), dim3(kMergeThreads), 0, s, mp));
+        CUDA_TRY(launch_pdl(idx->opt_pdl != 0, merge_topk_kernel, dim3(nq), dim3(kMergeThreads), 0, s, mp));
     }
     return B2S_OK;
 }
@@ -296,6 +323,7 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
     if ((int64_t)grid > units) grid = (int)units;
     grid = std::min(grid, kMergeMaxLists);
     const int max_group = scan_max_nq(idx->dim);
+    const bool pdl = idx->opt_pdl != 0;
 
     const int chunk = (int)std::min<int64_t>(nq, kScanQueryChunk);
     int rc;
@@ -303,10 +331,18 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
     if ((rc = idx->ws_counts.ensure((size_t)grid * chunk * sizeof(int))) != B2S_OK) return rc;
     if (seed && (rc = idx->ws_seed.ensure((size_t)chunk * sizeof(u64))) != B2S_OK) return rc;
 
-    // One scan launch covers the whole call and nothing is seeded: the last CTA of the scan does the
-    // merge (and, sharded with co-resident CTAs, the exchange) itself -- see scan_topk.cuh.
+    // One scan launch covers the whole call and nothing is seeded: the last CTA of the scan produces the
+    // final top-k (and, sharded with co-resident CTAs, the exchange) itself -- see scan_topk.cuh.
     const bool fuse_tail = idx->opt_fused_tail && !seed && nq <= max_group && idx->done_counter != nullptr &&
                            (idx->ex_call == nullptr || idx->ex_fused);
+    // Dynamic tail: the first S units of every CTA are static, the rest of the shard is dealt by ticket.
+    const int64_t full_units = idx->n / unit;
+    const int64_t static_units = std::max<int64_t>(0, full_units / grid - idx->opt_dynamic_tail);   // S
+    const bool dyn_ok = idx->opt_dynamic_tail > 0 && idx->work_counter != nullptr && idx->done_counter != nullptr;
+    const long long dyn_begin = dyn_ok ? (long long)(static_units * grid * unit) : (long long)idx->n;
+    // Cascade select: small k, one fused launch, enough static iterations for a meaningful phase A.
+    const bool cascade = idx->opt_cascade && fuse_tail && dyn_ok && idx->gslots != nullptr && k <= kCascadeMaxK &&
+                         static_units >= 8;
     for (int64_t c0 = 0; c0 < nq; c0 += chunk) {
         const int cn = (int)std::min<int64_t>(chunk, nq - c0);
         for (int pass = seed ? 0 : 1; pass < 2; ++pass) {
@@ -314,6 +350,7 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
                 int group = 1;
                 while (group * 2 <= max_group && g0 + group * 2 <= cn) group *= 2;
                 ScanParams p;
+                memset(&p, 0, offsetof(ScanParams, q_inline));
                 p.corpus = reinterpret_cast<const uint4*>(idx->rows);
                 p.queries = q_f32 + (size_t)c0 * idx->dim;
                 p.n_rows = idx->n;
@@ -329,16 +366,18 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
                 // The scan only READS the corpus and the caller's queries unless a kernel of THIS call
                 // ran before it (query prep, seeding pass, an earlier group writing the same workspace).
                 p.pdl_late_wait = (late_wait_ok && !seed && nq <= max_group) ? 1 : 0;
-                p.use_inline = 0;
+                p.done_counter = idx->done_counter;
+                p.work_counter = idx->work_counter;
+                p.dyn_begin = pass == 1 ? dyn_begin : (long long)idx->n;   // the sampling pre-pass is all static
+                p.prefetch_iters = pass == 1 ? std::min(32, std::max(0, idx->opt_prefetch_iters)) : 0;
+                p.trace = (idx->opt_trace && pass == 1) ? idx->trace_buf : nullptr;
+                p.early_trigger = idx->opt_pdl_early;
                 if (inline_q != nullptr) {
                     p.use_inline = 1;
                     memcpy(p.q_inline, inline_q, (size_t)nq * idx->dim * sizeof(float));
                 }
-                p.fused_tail = 0;
                 if (fuse_tail) {
                     p.fused_tail = idx->ex_call ? 2 : 1;
-                    p.done_counter = idx->done_counter;
-                    memset(&p.mp, 0, sizeof(p.mp));
                     p.mp.lists = p.lists;
                     p.mp.counts = p.counts;
                     p.mp.num_lists = grid;
@@ -350,15 +389,27 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
                     p.mp.out_scores = out_scores;
                     p.mp.out_ids = reinterpret_cast<long long*>(out_ids);
                     if (idx->ex_call) p.ex = *idx->ex_call;
+                    if (cascade) {
+                        p.select_mode = 1;
+                        p.gslots = idx->gslots;
+                        p.peek_every = idx->opt_peek_every;
+                        p.transition_mode = idx->opt_transition_mode;
+                        // phase A ends (and, with stable queries, the PDL wait sits) after a0 + blockIdx % stagger
+                        // iterations: early enough that the last CTA switches over in the first half of the scan
+                        int a = idx->opt_phase_a > 0 ? idx->opt_phase_a : std::max(2, std::min((int)(static_units / 8), 8));
+                        p.phase_a_iters = (int)std::min<int64_t>(a, static_units);
+                        p.phase_a_stagger = (int)std::max<int64_t>(1, std::min<int64_t>(idx->opt_phase_a_stagger,
+                                                                                         static_units / 2 - p.phase_a_iters));
+                    }
                 }
-                if ((rc = launch_scan(idx->dim, group, p, grid, s)) != B2S_OK) return rc;
+                if ((rc = launch_scan(idx->dim, group, p, grid, s, pdl)) != B2S_OK) return rc;
                 idx->stats.kernel_launches++;
                 if (pass == 1) idx->stats.passes++;
                 g0 += group;
             }
             if (fuse_tail) {
                 if (idx->time_this) cudaEventRecord(idx->ev[2], s);
-                continue;   // merged (and exchanged) by the scan kernel's last CTA
+                continue;   // finished (and exchanged) by the scan kernel's last CTA
             }
             MergeParams mp;
             memset(&mp, 0, sizeof(mp));
@@ -503,9 +554,13 @@ int search_core(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, in
             qf = reinterpret_cast<const float*>(idx->ws_qf32.p);
         }
         if (idx->time_this) cudaEventRecord(idx->ev[1], s);
-        // late PDL wait only if no kernel of this call precedes the scan and no event sits between
-        // consecutive calls' kernels (timing on) -- see scan_topk.cuh
-        const bool late_wait_ok = (qf == reinterpret_cast<const float*>(queries)) && idx->opt_pdl == 2;
+        // Late PDL wait (the scan overlaps the tail of the previous kernel of the stream) only when nothing the
+        // scan reads early can have been produced by that kernel: the query rides in the parameters (host
+        // call), or the caller vouches for its buffer (B2S_SEARCH_STABLE_QUERIES / option pdl = 2) and no
+        // kernel of this call precedes the scan -- see scan_topk.cuh
+        const bool stable = (idx->call_flags & B2S_SEARCH_STABLE_QUERIES) != 0 || idx->opt_pdl == 2;
+        const bool late_wait_ok = idx->opt_pdl != 0 &&
+                                  (inline_q != nullptr || (stable && qf == reinterpret_cast<const float*>(queries)));
         rc = search_scan(idx, qf, nq, k, out_scores, out_ids, s, seed, late_wait_ok, inline_q);
         if (rc != B2S_OK) return rc;
     } else {
@@ -541,6 +596,29 @@ int search_impl(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, in
     return B2S_OK;
 }
 
+// The workspaces (lists, counters, slots) belong to the handle, not to a stream: a search enqueued on
+// another stream than the previous one first waits for everything enqueued on that stream so far.
+int guard_stream(b2s_index* idx, cudaStream_t s) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) cudaGetLastError();
+    // A search captured into a CUDA graph is ordered by whoever launches the graph: nothing outside the
+    // capture may be waited for here (and the graph may be replayed on any stream later).
+    if (cap != cudaStreamCaptureStatusNone) return B2S_OK;
+    if (idx->last_stream_valid && idx->last_stream != s) {
+        cudaError_t e = cudaSuccess;
+        if (!idx->xs_event) e = cudaEventCreateWithFlags(&idx->xs_event, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(idx->xs_event, idx->last_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, idx->xs_event, 0);
+        if (e != cudaSuccess) {   // e.g. the previous stream was destroyed by its owner
+            cudaGetLastError();
+            CUDA_TRY(cudaDeviceSynchronize());
+        }
+    }
+    idx->last_stream = s;
+    idx->last_stream_valid = true;
+    return B2S_OK;
+}
+
 int ensure_pinned(void** p, size_t* have, size_t need) {
     if (need <= *have) return B2S_OK;
     if (*p) cudaFreeHost(*p);
@@ -572,16 +650,18 @@ static void exchange_release(b2s_index* idx) {
     for (void* m : ex.opened) cudaIpcCloseMemHandle(m);
     ex.opened.clear();
     if (ex.peers_dev) cudaFree(ex.peers_dev);
-    if (ex.status) cudaFree(ex.status);
+    if (ex.status) cudaFreeHost(ex.status);
     if (ex.local) cudaFree(ex.local);
+    const long long keep_timeout = ex.timeout_ms;
     ex = b2s_index::Exchange();
+    ex.timeout_ms = keep_timeout;
     cudaGetLastError();
 }
 
 
 extern "C" {
 
-B2S_API int b2s_version(void) { return 101; }
+B2S_API int b2s_version(void) { return 200; }
 
 B2S_API const char* b2s_last_error(void) { return g_err.c_str(); }
 
@@ -625,10 +705,16 @@ B2S_API int b2s_create(int dim, int metric, int device, b2s_index** out) {
         delete idx;
         return fail(B2S_ERR_CUDA, "cudaStreamCreate failed");
     }
-    if (cudaMalloc((void**)&idx->done_counter, sizeof(unsigned)) != cudaSuccess ||
-        cudaMemset(idx->done_counter, 0, sizeof(unsigned)) != cudaSuccess) {
+    // [done ticket | kScanWarps work counters, one 128-byte line each | global slots of the cascade select]
+    constexpr size_t kSlotsOff = 128 * (1 + kScanWarps);
+    constexpr size_t kCtlBytes = kSlotsOff + (size_t)kScanMaxNQ * kCascadeMaxK * sizeof(u64);
+    if (cudaMalloc((void**)&idx->done_counter, kCtlBytes) != cudaSuccess ||
+        cudaMemset(idx->done_counter, 0, kCtlBytes) != cudaSuccess) {
         cudaGetLastError();
-        idx->done_counter = nullptr;   // the fused tail is simply not used
+        idx->done_counter = nullptr;   // the fused tail, the dynamic tail and the cascade select are simply not used
+    } else {
+        idx->work_counter = idx->done_counter + kWorkCounterStride;
+        idx->gslots = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(idx->done_counter) + kSlotsOff);
     }
     *out = idx;
     return B2S_OK;
@@ -659,6 +745,8 @@ B2S_API int b2s_destroy(b2s_index* idx) {
 #endif
     exchange_release(idx);
     if (idx->done_counter) cudaFree(idx->done_counter);
+    if (idx->trace_buf) cudaFree(idx->trace_buf);
+    if (idx->xs_event) cudaEventDestroy(idx->xs_event);
     if (idx->pin_q) cudaFreeHost(idx->pin_q);
     if (idx->pin_out) cudaFreeHost(idx->pin_out);
     if (idx->ring) {
@@ -680,7 +768,7 @@ B2S_API int b2s_reserve(b2s_index* idx, int64_t n_rows) {
     return grow_rows(idx, n_rows);
 }
 
-static int add_impl(b2s_index* idx, const void* rows, int64_t n, int is_device, bool is_bf16) {
+static int add_impl(b2s_index* idx, const void* rows, int64_t n, int is_device, bool is_bf16, bool prepared = false) {
     if (!idx) return fail(B2S_ERR_INVALID, "null index");
     if (n < 0) return fail(B2S_ERR_INVALID, "n < 0");
     if (n == 0) return B2S_OK;
@@ -692,7 +780,7 @@ static int add_impl(b2s_index* idx, const void* rows, int64_t n, int is_device, 
     if ((rc = grow_rows(idx, idx->n + n)) != B2S_OK) return rc;
     const int dim = idx->dim;
     const size_t esz = is_bf16 ? 2 : 4;
-    const bool normalize = idx->metric == B2S_METRIC_COSINE;
+    const bool normalize = idx->metric == B2S_METRIC_COSINE && !prepared;
     const int64_t chunk_rows = std::max<int64_t>(1, ((int64_t)256 << 20) / ((int64_t)dim * (int64_t)esz));
     for (int64_t r0 = 0; r0 < n; r0 += chunk_rows) {
         const int64_t rn = std::min<int64_t>(chunk_rows, n - r0);
@@ -748,6 +836,11 @@ B2S_API int b2s_add_f32(b2s_index* idx, const float* rows, int64_t n, int is_dev
 }
 B2S_API int b2s_add_bf16(b2s_index* idx, const void* rows, int64_t n, int is_device) {
     return add_impl(idx, rows, n, is_device, true);
+}
+
+B2S_API int b2s_add_prepared(b2s_index* idx, const void* rows, int q_dtype, int64_t n, int is_device) {
+    if (q_dtype != B2S_DTYPE_F32 && q_dtype != B2S_DTYPE_BF16) return fail(B2S_ERR_INVALID, "bad dtype");
+    return add_impl(idx, rows, n, is_device, q_dtype == B2S_DTYPE_BF16, true);
 }
 
 B2S_API int64_t b2s_ntotal(const b2s_index* idx) { return idx ? idx->n : 0; }
@@ -810,7 +903,40 @@ B2S_API int b2s_set_option(b2s_index* idx, const char* name, int64_t value) {
     } else if (s == "pdl") {
         if (value < 0 || value > 2) return fail(B2S_ERR_INVALID, "pdl must be 0, 1 or 2");
         idx->opt_pdl = (int)value;
-        g_pdl_enabled = value != 0;
+    } else if (s == "exchange_timeout_ms") {
+        if (value < 1 || value > 600000) return fail(B2S_ERR_INVALID, "exchange_timeout_ms must be in [1, 600000]");
+        idx->ex.timeout_ms = value;
+    } else if (s == "prefetch_iters") {
+        if (value < 0 || value > 32) return fail(B2S_ERR_INVALID, "prefetch_iters must be in [0, 32]");
+        idx->opt_prefetch_iters = (int)value;
+    } else if (s == "dynamic_tail") {
+        if (value < 0 || value > 64) return fail(B2S_ERR_INVALID, "dynamic_tail must be in [0, 64]");
+        idx->opt_dynamic_tail = (int)value;
+    } else if (s == "cascade") {
+        idx->opt_cascade = value ? 1 : 0;
+    } else if (s == "phase_a") {
+        if (value < 0 || value > 4096) return fail(B2S_ERR_INVALID, "phase_a must be in [0, 4096]");
+        idx->opt_phase_a = (int)value;
+    } else if (s == "transition_mode") {
+        if (value < 0 || value > 2) return fail(B2S_ERR_INVALID, "transition_mode must be 0, 1 or 2");
+        idx->opt_transition_mode = (int)value;
+    } else if (s == "peek_every") {
+        if (value < 0 || value > 4096) return fail(B2S_ERR_INVALID, "peek_every must be in [0, 4096]");
+        idx->opt_peek_every = (int)value;
+    } else if (s == "phase_a_stagger") {
+        if (value < 1 || value > 4096) return fail(B2S_ERR_INVALID, "phase_a_stagger must be in [1, 4096]");
+        idx->opt_phase_a_stagger = (int)value;
+    } else if (s == "pdl_early") {
+        idx->opt_pdl_early = value ? 1 : 0;
+    } else if (s == "trace") {
+        if (value && !idx->trace_buf) {
+            int rc = use_device(idx);
+            if (rc != B2S_OK) return rc;
+            const size_t bytes = (size_t)(kTraceWords + kTraceArrays * kTraceStride) * sizeof(unsigned long long);
+            CUDA_TRY(cudaMalloc((void**)&idx->trace_buf, bytes));
+            CUDA_TRY(cudaMemset(idx->trace_buf, 0, bytes));
+        }
+        idx->opt_trace = value ? 1 : 0;
     } else if (s == "tc_sample_div") {
         idx->opt_tc_sample_div = (int)std::min<int64_t>(1 << 20, std::max<int64_t>(0, value));
     } else if (s == "tc_shared_thr") {
@@ -839,6 +965,16 @@ B2S_API int64_t b2s_get_option(const b2s_index* idx, const char* name) {
     if (s == "timing") return idx->opt_timing;
     if (s == "tc_min_nq") return idx->opt_tc_min_nq;
     if (s == "pdl") return idx->opt_pdl;
+    if (s == "prefetch_iters") return idx->opt_prefetch_iters;
+    if (s == "dynamic_tail") return idx->opt_dynamic_tail;
+    if (s == "cascade") return idx->opt_cascade;
+    if (s == "phase_a") return idx->opt_phase_a;
+    if (s == "phase_a_stagger") return idx->opt_phase_a_stagger;
+    if (s == "trace") return idx->opt_trace;
+    if (s == "pdl_early") return idx->opt_pdl_early;
+    if (s == "transition_mode") return idx->opt_transition_mode;
+    if (s == "peek_every") return idx->opt_peek_every;
+    if (s == "exchange_timeout_ms") return idx->ex.timeout_ms;
     if (s == "fused_tail") return idx->opt_fused_tail;
     if (s == "tc_sample_div") return idx->opt_tc_sample_div;
     if (s == "tc_shared_thr") return idx->opt_tc_shared_thr;
@@ -848,10 +984,18 @@ B2S_API int64_t b2s_get_option(const b2s_index* idx, const char* name) {
 }
 
 B2S_API int b2s_search_device(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, int k,
-                              float* out_scores, int64_t* out_ids, void* cuda_stream) {
+                              float* out_scores, int64_t* out_ids, void* cuda_stream, unsigned flags) {
     if (!idx) return fail(B2S_ERR_INVALID, "null index");
+    if (flags & ~(unsigned)B2S_SEARCH_STABLE_QUERIES) return fail(B2S_ERR_INVALID, "unknown search flag");
     std::lock_guard<std::mutex> g(idx->mu);
-    return search_impl(idx, queries, q_dtype, nq, k, out_scores, out_ids, reinterpret_cast<cudaStream_t>(cuda_stream));
+    int rc = use_device(idx);
+    if (rc != B2S_OK) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    if ((rc = guard_stream(idx, s)) != B2S_OK) return rc;
+    idx->call_flags = flags;
+    rc = search_impl(idx, queries, q_dtype, nq, k, out_scores, out_ids, s);
+    idx->call_flags = 0;
+    return rc;
 }
 
 // Host-buffer search shared by b2s_search and b2s_search_sharded.  Three regimes:
@@ -866,6 +1010,7 @@ static int search_host(b2s_index* idx, const float* queries, int64_t nq, int k, 
                        bool sharded) {
     int rc = use_device(idx);
     if (rc != B2S_OK) return rc;
+    if ((rc = guard_stream(idx, idx->stream)) != B2S_OK) return rc;
     const size_t qbytes = (size_t)nq * idx->dim * sizeof(float);
     const size_t sbytes = (size_t)nq * k * sizeof(float);
     const size_t ibytes = (size_t)nq * k * sizeof(int64_t);
@@ -909,6 +1054,9 @@ static int search_host(b2s_index* idx, const float* queries, int64_t nq, int k, 
         CUDA_TRY(cudaMemcpyAsync(out_scores, io_scores, sbytes, cudaMemcpyDeviceToHost, idx->stream));
         CUDA_TRY(cudaStreamSynchronize(idx->stream));
     }
+    if (sharded && idx->ex.status && *(volatile unsigned*)idx->ex.status != 0u)
+        return fail(B2S_ERR_CUDA, "sharded search: timed out waiting for a peer rank's candidates (call #" +
+                                      std::to_string(*(volatile unsigned*)idx->ex.status) + "); the results are invalid");
     return B2S_OK;
 }
 
@@ -927,8 +1075,7 @@ B2S_API int b2s_merge_device(int device, const float* scores, const int64_t* ids
     if (g < 1 || nq < 0 || k < 0) return fail(B2S_ERR_INVALID, "bad arguments");
     if (nq == 0 || k == 0) return B2S_OK;
     if (!scores || !ids || !out_scores || !out_ids) return fail(B2S_ERR_INVALID, "null buffer");
-    if ((int64_t)g * k > kMergeSortCap)
-        return fail(B2S_ERR_UNSUPPORTED, "g * k exceeds the merge buffer (4096 candidates per query)");
+    if ((int64_t)g * k > (int64_t)1 << 24) return fail(B2S_ERR_UNSUPPORTED, "g * k too large");
     CUDA_TRY(cudaSetDevice(device));
     MergeParams mp;
     memset(&mp, 0, sizeof(mp));
@@ -947,6 +1094,20 @@ B2S_API int b2s_merge_device(int device, const float* scores, const int64_t* ids
     return B2S_OK;
 }
 
+// compute_similarity has no index handle: its device buffers, pinned staging and stream are cached per device
+// (ANCEMiner.mine calls it twice per query with a 1 x <= 20 problem: no allocation in steady state).
+namespace {
+struct SimWorkspace {
+    DevBuf q, d, out;
+    void* pin = nullptr;
+    size_t pin_bytes = 0;
+    cudaStream_t stream = nullptr;
+    bool attr_set = false;
+};
+std::mutex g_sim_mu;
+SimWorkspace g_sim[64];
+}  // namespace
+
 B2S_API int b2s_similarity(int device, const float* q, int64_t nq, const float* d, int64_t nd, int dim,
                            float* out) {
     if (nq < 0 || nd < 0 || dim <= 0) return fail(B2S_ERR_INVALID, "bad arguments");
@@ -958,33 +1119,38 @@ B2S_API int b2s_similarity(int device, const float* q, int64_t nq, const float* 
         cudaGetLastError();
         return fail(B2S_ERR_NO_DEVICE, "no CUDA device: libb200search has no CPU fallback");
     }
+    if (device < 0 || device >= ndev || device >= 64) return fail(B2S_ERR_INVALID, "device ordinal out of range");
     CUDA_TRY(cudaSetDevice(device));
-    float *dq = nullptr, *dd = nullptr, *ds = nullptr;
-    int rc = B2S_OK;
-    cudaError_t e;
-    if ((e = cudaMalloc((void**)&dq, (size_t)nq * dim * 4)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&dd, (size_t)nd * dim * 4)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&ds, (size_t)nq * nd * 4)) != cudaSuccess) {
-        rc = fail(B2S_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    std::lock_guard<std::mutex> g(g_sim_mu);
+    SimWorkspace& w = g_sim[device];
+    if (!w.stream) CUDA_TRY(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    const size_t qb = (size_t)nq * dim * 4, db = (size_t)nd * dim * 4, ob = (size_t)nq * nd * 4;
+    int rc;
+    if ((rc = w.q.ensure(qb)) != B2S_OK || (rc = w.d.ensure(db)) != B2S_OK || (rc = w.out.ensure(ob)) != B2S_OK) return rc;
+    const size_t smem = (size_t)dim * 8 * sizeof(float);
+    if (smem > 48 * 1024 && !w.attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(similarity_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        w.attr_set = true;
     }
-    if (rc == B2S_OK) {
-        const size_t smem = (size_t)dim * 8 * sizeof(float);
-        e = cudaMemcpy(dq, q, (size_t)nq * dim * 4, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(dd, d, (size_t)nd * dim * 4, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess && smem > 48 * 1024)
-            e = cudaFuncSetAttribute(similarity_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) {
-            similarity_f32_kernel<<<(unsigned)((nd + 7) / 8), 256, smem>>>(dq, nq, dd, nd, dim, ds);
-            e = cudaGetLastError();
-        }
-        if (e == cudaSuccess) e = cudaMemcpy(out, ds, (size_t)nq * nd * 4, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) rc = fail(B2S_ERR_CUDA, std::string("similarity: ") + cudaGetErrorString(e));
+    // small problems go through pinned staging (true DMA, one synchronise); large ones copy from the caller's buffers
+    const bool small = qb + db + ob <= ((size_t)1 << 20);
+    unsigned char* pin = nullptr;
+    if (small) {
+        if ((rc = ensure_pinned(&w.pin, &w.pin_bytes, qb + db + ob)) != B2S_OK) return rc;
+        pin = reinterpret_cast<unsigned char*>(w.pin);
+        memcpy(pin, q, qb);
+        memcpy(pin + qb, d, db);
     }
-    cudaFree(dq);
-    cudaFree(dd);
-    cudaFree(ds);
-    cudaGetLastError();
-    return rc;
+    CUDA_TRY(cudaMemcpyAsync(w.q.p, small ? (const void*)pin : (const void*)q, qb, cudaMemcpyHostToDevice, w.stream));
+    CUDA_TRY(cudaMemcpyAsync(w.d.p, small ? (const void*)(pin + qb) : (const void*)d, db, cudaMemcpyHostToDevice, w.stream));
+    similarity_f32_kernel<<<(unsigned)((nd + 7) / 8), 256, smem, w.stream>>>(
+        reinterpret_cast<const float*>(w.q.p), nq, reinterpret_cast<const float*>(w.d.p), nd, dim,
+        reinterpret_cast<float*>(w.out.p));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(small ? (void*)(pin + qb + db) : (void*)out, w.out.p, ob, cudaMemcpyDeviceToHost, w.stream));
+    CUDA_TRY(cudaStreamSynchronize(w.stream));
+    if (small) memcpy(out, pin + qb + db, ob);
+    return B2S_OK;
 }
 
 B2S_API int b2s_read_rows_f32(b2s_index* idx, int64_t start, int64_t n, float* out_host) {
@@ -1027,6 +1193,18 @@ B2S_API int b2s_read_timings(const b2s_index* idx, float* dominant_ms, float* to
     return n;
 }
 
+B2S_API int b2s_read_trace(b2s_index* idx, uint64_t* out, int max_words) {
+    if (!idx || !out || max_words < 0) return fail(B2S_ERR_INVALID, "bad arguments");
+    if (!idx->trace_buf) return 0;
+    std::lock_guard<std::mutex> g(idx->mu);
+    int rc = use_device(idx);
+    if (rc != B2S_OK) return rc;
+    const int n = std::min(max_words, kTraceWords + kTraceArrays * kTraceStride);
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out, idx->trace_buf, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return n;
+}
+
 B2S_API int b2s_merge_packed_device(int device, const void* packed, int g, int64_t nq, int k, float* out_scores,
                                     int64_t* out_ids, void* cuda_stream) {
     if (!packed) return fail(B2S_ERR_INVALID, "null buffer");
@@ -1035,8 +1213,7 @@ B2S_API int b2s_merge_packed_device(int device, const void* packed, int g, int64
     if (g < 1 || nq < 0 || k < 0) return fail(B2S_ERR_INVALID, "bad arguments");
     if (nq == 0 || k == 0) return B2S_OK;
     if (!out_scores || !out_ids) return fail(B2S_ERR_INVALID, "null buffer");
-    if ((int64_t)g * k > kMergeSortCap)
-        return fail(B2S_ERR_UNSUPPORTED, "g * k exceeds the merge buffer (4096 candidates per query)");
+    if ((int64_t)g * k > (int64_t)1 << 24) return fail(B2S_ERR_UNSUPPORTED, "g * k too large");
     CUDA_TRY(cudaSetDevice(device));
     MergeParams mp;
     memset(&mp, 0, sizeof(mp));
@@ -1146,8 +1323,15 @@ B2S_API int b2s_exchange_create(b2s_index* idx, int world, int rank, int64_t slo
     ex.bytes = (size_t)ex.ll_off + (size_t)2 * world * (size_t)ex.ll_entries * 24;
     CUDA_TRY(cudaMalloc((void**)&ex.local, ex.bytes));
     CUDA_TRY(cudaMemset(ex.local, 0, ex.bytes));
-    CUDA_TRY(cudaMalloc((void**)&ex.status, sizeof(unsigned)));
-    CUDA_TRY(cudaMemset(ex.status, 0, sizeof(unsigned)));
+    CUDA_TRY(cudaHostAlloc((void**)&ex.status, sizeof(unsigned), cudaHostAllocMapped | cudaHostAllocPortable));
+    *ex.status = 0u;
+    {
+        // the fused kernel's CTAs push before they wait, but a CTA that is not resident cannot push: keep the
+        // fused grid within what the device holds at once (and never above one CTA per SM)
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_exchange_kernel<true>, kMergeThreads, 0));
+        ex.max_fused_nq = std::min(idx->num_sms, per_sm * idx->num_sms);
+    }
     CUDA_TRY(cudaMalloc((void**)&ex.peers_dev, sizeof(unsigned char*) * world));
     CUDA_TRY(cudaDeviceSynchronize());
     if (ipc_handle_out) {
@@ -1191,24 +1375,30 @@ B2S_API int b2s_exchange_connect(b2s_index* idx, const void* handles, int raw_po
 
 B2S_API int b2s_exchange_status(b2s_index* idx) {
     if (!idx || !idx->ex.status) return 0;
-    unsigned v = 0;
     cudaSetDevice(idx->device);
-    if (cudaMemcpy(&v, idx->ex.status, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    if (cudaDeviceSynchronize() != cudaSuccess) {
         cudaGetLastError();
         return -1;
     }
-    return (int)v;
+    return (int)*(volatile unsigned*)idx->ex.status;
 }
 
 static int search_sharded_impl(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, int k,
                                float* out_scores, int64_t* out_ids, void* cuda_stream, int phase) {
     auto& ex = idx->ex;
     if (!ex.connected) return fail(B2S_ERR_INVALID, "exchange is not connected");
-    if (nq > ex.max_nq || b2s_packed_bytes(nq, k) > ex.slot_stride || (int64_t)ex.world * k > kMergeSortCap)
+    if (nq > ex.max_nq || b2s_packed_bytes(nq, k) > ex.slot_stride)
         return fail(B2S_ERR_UNSUPPORTED, "sharded search: (nq, k) exceeds the exchange buffer; use the all-gather path");
+    if (idx->opt_keep_f32 && idx->rows_f32)
+        return fail(B2S_ERR_UNSUPPORTED, "sharded search: fp32 re-ranking (keep_f32) is not applied before the peer "
+                                         "exchange; use the all-gather path");
+    if (const unsigned bad = *(volatile unsigned*)ex.status)
+        return fail(B2S_ERR_CUDA, "sharded search: call #" + std::to_string(bad) + " timed out waiting for a peer rank; "
+                                  "its results were invalid (re-create the exchange)");
     int rc = use_device(idx);
     if (rc != B2S_OK) return rc;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    if ((rc = guard_stream(idx, s)) != B2S_OK) return rc;
     ExchangeArgs a;
     memset(&a, 0, sizeof(a));
     a.peer_base = ex.peers_dev;
@@ -1219,22 +1409,26 @@ static int search_sharded_impl(b2s_index* idx, const void* queries, int q_dtype,
     a.flags_off = ex.flags_off;
     a.max_nq = ex.max_nq;
     a.nq = nq;
-    a.timeout_cycles = 60000000000ll;  // ~30 s of SM clock: ranks may be skewed by host work, but a missing
-                                       // peer must not hang the GPU for ever (the status word reports it)
+    a.timeout_cycles = ex.timeout_ms * 2000000ll;   // SM clock ~2 GHz: ranks may be skewed by host work, but a
+                                                    // missing peer must not hang the GPU (the status word reports it)
     a.status = ex.status;
     a.out_scores = out_scores;
     a.out_ids = reinterpret_cast<long long*>(out_ids);
     if (phase != 2) {
         a.seq = ++ex.seq;
         // one kernel when every CTA of the merge is co-resident on every rank, else push / wait split
-        idx->ex_fused = (phase == 0 && nq <= idx->num_sms) ? 1 : 0;
-        a.use_ll = (idx->ex_fused && idx->opt_exchange_ll && nq * (int64_t)k <= ex.ll_entries) ? 1 : 0;
+        idx->ex_fused = (phase == 0 && nq <= ex.max_fused_nq) ? 1 : 0;
+        a.use_ll = (idx->ex_fused && idx->opt_exchange_ll && nq * (int64_t)k <= ex.ll_entries &&
+                    (int64_t)ex.world * k <= kMergeSortCap) ? 1 : 0;
         a.ll_off = ex.ll_off;
         a.ll_entries = ex.ll_entries;
         idx->ex_call = &a;
         rc = search_impl(idx, queries, q_dtype, nq, k, out_scores, out_ids, s);
         idx->ex_call = nullptr;
-        if (rc != B2S_OK) return rc;
+        if (rc != B2S_OK) {
+            if (idx->stats.kernel_launches == 0) --ex.seq;   // nothing was enqueued: the ranks stay in step
+            return rc;
+        }
         if (idx->ex_fused || phase == 1) return B2S_OK;
     } else {
         a.seq = ex.seq;
@@ -1246,13 +1440,18 @@ static int search_sharded_impl(b2s_index* idx, const void* queries, int q_dtype,
 }
 
 B2S_API int b2s_search_sharded_device(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, int k,
-                                      float* out_scores, int64_t* out_ids, void* cuda_stream, int phase) {
+                                      float* out_scores, int64_t* out_ids, void* cuda_stream, int phase,
+                                      unsigned flags) {
     if (!idx) return fail(B2S_ERR_INVALID, "null index");
     if (nq < 0 || k < 0) return fail(B2S_ERR_INVALID, "nq and k must be >= 0");
     if (nq == 0 || k == 0) return B2S_OK;
     if (phase < 0 || phase > 2) return fail(B2S_ERR_INVALID, "phase must be 0 (whole call), 1 (push) or 2 (wait+merge)");
+    if (flags & ~(unsigned)B2S_SEARCH_STABLE_QUERIES) return fail(B2S_ERR_INVALID, "unknown search flag");
     std::lock_guard<std::mutex> g(idx->mu);
-    return search_sharded_impl(idx, queries, q_dtype, nq, k, out_scores, out_ids, cuda_stream, phase);
+    idx->call_flags = phase == 0 ? flags : 0u;
+    const int rc = search_sharded_impl(idx, queries, q_dtype, nq, k, out_scores, out_ids, cuda_stream, phase);
+    idx->call_flags = 0;
+    return rc;
 }
 
 B2S_API int b2s_search_sharded(b2s_index* idx, const float* queries, int64_t nq, int k, float* out_scores,

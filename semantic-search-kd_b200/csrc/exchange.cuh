@@ -37,7 +37,7 @@ struct ExchangeArgs {
     long long nq;                      // queries of the whole call
     int q_offset;                      // global index of this launch's query 0
     long long timeout_cycles;          // spin budget; on expiry *status = seq and the result is garbage
-    unsigned* status;                  // device word, 0 = ok
+    unsigned* status;                  // mapped pinned host word, 0 = ok
     float* out_scores;                 // [nq, k] final
     long long* out_ids;
     // low-latency protocol (fused mode): candidates travel as three 8-byte words, each tagged with the
@@ -100,17 +100,28 @@ __device__ __forceinline__ void exchange_wait_merge(const ExchangeArgs& ex, int 
         const long long t0 = clock64();
         while (ld_acquire_sys_u32(flag) != ex.seq) {
             if (clock64() - t0 > ex.timeout_cycles) {
-                atomicExch(ex.status, ex.seq);
+                *(volatile unsigned*)ex.status = ex.seq;   // mapped host word
                 break;
             }
             __nanosleep(64);
         }
     }
     __syncthreads();
-    const int total = ex.world * k;   // host guarantees total <= kMergeSortCap
+    const int total = ex.world * k;
+    auto slot_of = [&](int r) { return ex.local_base + ((long long)parity * ex.world + r) * ex.slot_stride; };
+    if (total > kMergeSortCap) {
+        // large k on many ranks (e.g. 8 x 1000): every rank's block is sorted, so a candidate's global rank is
+        // its own position plus, per other rank, a binary search -- no shared-memory staging at all
+        merge_runs_bsearch<NT>(
+            ex.world, k, k,
+            [&](int r, int i) { return __ldcg(reinterpret_cast<const float*>(slot_of(r) + ex.nq * k * 8 + (gq * k + i) * 4)); },
+            [&](int r, int i) { return __ldcg(reinterpret_cast<const long long*>(slot_of(r) + (gq * k + i) * 8)); },
+            ex.out_scores + gq * k, ex.out_ids + gq * k);
+        return;
+    }
     for (int e = tid; e < total; e += NT) {
         const int r = e / k, i = e - r * k;
-        const unsigned char* slot = ex.local_base + ((long long)parity * ex.world + r) * ex.slot_stride;
+        const unsigned char* slot = slot_of(r);
         const long long id = __ldcg(reinterpret_cast<const long long*>(slot + (gq * k + i) * 8));
         const float s = __ldcg(reinterpret_cast<const float*>(slot + ex.nq * k * 8 + (gq * k + i) * 4));
         // position e = rank-major, then local order: keeps (score desc, id asc) across shards
@@ -124,7 +135,7 @@ __device__ __forceinline__ void exchange_wait_merge(const ExchangeArgs& ex, int 
         if (i < total && buf[i] != 0ull) {
             const int pos = (int)key_row(buf[i]);
             const int r = pos / k, j = pos - r * k;
-            const unsigned char* slot = ex.local_base + ((long long)parity * ex.world + r) * ex.slot_stride;
+            const unsigned char* slot = slot_of(r);
             id = __ldcg(reinterpret_cast<const long long*>(slot + (gq * k + j) * 8));
             s = __ldcg(reinterpret_cast<const float*>(slot + ex.nq * k * 8 + (gq * k + j) * 4));
         }
@@ -167,33 +178,76 @@ __device__ __forceinline__ void exchange_push_ll(const ExchangeArgs& ex, const M
     }
 }
 
-// LL wait + merge: every thread polls its own candidate's three words in local memory.
+// LL wait + merge: every thread polls its own candidate's three words in local memory (ONE deadline for
+// the whole call: a missing peer costs timeout_cycles once, not once per candidate).
+constexpr int kExchangeRankSortMax = 1024;
 template <int NT = 512>
-__device__ __forceinline__ void exchange_wait_merge_ll(const ExchangeArgs& ex, int k, u64* buf, long long gq) {
+__device__ __forceinline__ void exchange_wait_merge_ll(const ExchangeArgs& ex, int k, u64* buf, long long gq,
+                                                       unsigned long long* tr = nullptr) {
+    __shared__ int s_valid;
     const int tid = threadIdx.x;
     const int parity = (int)(ex.seq & 1u);
     const int total = ex.world * k;   // host guarantees total <= kMergeSortCap
     const u64* ll = reinterpret_cast<const u64*>(ex.local_base + ex.ll_off);
+    if (tid == 0) s_valid = 0;
+    const long long t0 = clock64();
+    float s_first = -FLT_MAX;         // this thread's first candidate stays in registers (total <= NT: the only one)
+    long long id_first = -1;
     for (int e = tid; e < total; e += NT) {
         const int r = e / k, i = e - r * k;
         const u64* src = ll + (((long long)parity * ex.world + r) * ex.ll_entries + gq * k + i) * 3;
         u64 w0, w1, w2;
-        const long long t0 = clock64();
         while (true) {
             w0 = ld_relaxed_sys_u64(src);
             w1 = ld_relaxed_sys_u64(src + 1);
             w2 = ld_relaxed_sys_u64(src + 2);
             if ((uint32_t)(w0 >> 32) == ex.seq && (uint32_t)(w1 >> 32) == ex.seq && (uint32_t)(w2 >> 32) == ex.seq) break;
             if (clock64() - t0 > ex.timeout_cycles) {
-                atomicExch(ex.status, ex.seq);
+                *(volatile unsigned*)ex.status = ex.seq;   // mapped host word
                 w1 = w2 = 0xffffffffull;   // id -1: ignored
                 break;
             }
         }
         const long long id = (long long)(((u64)(uint32_t)w2 << 32) | (u64)(uint32_t)w1);
-        buf[e] = id < 0 ? 0ull : make_key(__uint_as_float((uint32_t)w0), (uint32_t)e);
+        const float sc = __uint_as_float((uint32_t)w0);
+        buf[e] = id < 0 ? 0ull : make_key(sc, (uint32_t)e);
+        if (e == tid) {
+            s_first = sc;
+            id_first = id;
+        }
     }
     __syncthreads();
+    if (tr) tr[4] = globaltimer_ns();
+    if (total <= kExchangeRankSortMax) {
+        // rank sort: keys are unique (position is the tie-break), a valid key's rank is its output slot
+        int mine_valid = 0;
+        for (int e = tid; e < total; e += NT) {
+            const u64 key = buf[e];
+            if (key == 0ull) continue;
+            ++mine_valid;
+            int rank = 0;
+            for (int j = 0; j < total; ++j) rank += buf[j] > key;
+            if (rank < k) {
+                float sc = s_first;
+                long long id = id_first;
+                if (e != tid) {
+                    const int r = e / k, i = e - r * k;
+                    const u64* src = ll + (((long long)parity * ex.world + r) * ex.ll_entries + gq * k + i) * 3;
+                    sc = __uint_as_float((uint32_t)__ldcg(src));
+                    id = (long long)(((u64)(uint32_t)__ldcg(src + 2) << 32) | (u64)(uint32_t)__ldcg(src + 1));
+                }
+                ex.out_scores[gq * k + rank] = sc;
+                ex.out_ids[gq * k + rank] = id;
+            }
+        }
+        if (mine_valid) atomicAdd(&s_valid, mine_valid);
+        __syncthreads();
+        for (int i = s_valid + tid; i < k; i += NT) {
+            ex.out_scores[gq * k + i] = -FLT_MAX;
+            ex.out_ids[gq * k + i] = -1;
+        }
+        return;
+    }
     block_sort_desc<NT>(buf, total > 0 ? total : 1, tid);
     for (int i = tid; i < k; i += NT) {
         float s = -FLT_MAX;
@@ -212,11 +266,13 @@ __device__ __forceinline__ void exchange_wait_merge_ll(const ExchangeArgs& ex, i
 
 // push + wait + merge of one query inside a block that holds its sorted local top-k in buf
 template <int NT = 512>
-__device__ __forceinline__ void exchange_fused(const ExchangeArgs& ex, const MergeParams& p, u64* buf, int kk, long long gq) {
+__device__ __forceinline__ void exchange_fused(const ExchangeArgs& ex, const MergeParams& p, u64* buf, int kk, long long gq,
+                                               unsigned long long* tr = nullptr) {
     if (ex.use_ll) {
         exchange_push_ll<NT>(ex, p, buf, kk, gq);
         __syncthreads();
-        exchange_wait_merge_ll<NT>(ex, p.k, buf, gq);
+        if (tr) tr[3] = globaltimer_ns();
+        exchange_wait_merge_ll<NT>(ex, p.k, buf, gq, tr);
     } else {
         exchange_push<NT>(ex, p, buf, kk, gq);
         __syncthreads();

@@ -46,7 +46,7 @@ int tc_encode_rows(b2s_index* idx, CUtensorMap* map, const void* base, uint64_t 
 
 // K2 launch: 2-CTA clusters for the pair variant, plain grid for the single-CTA variant.
 template <bool PREPASS, bool PAIR>
-cudaError_t tc_launch(int ctas, size_t smem, cudaStream_t s, const CUtensorMap& corpus, const CUtensorMap& queries,
+cudaError_t tc_launch(bool pdl, int ctas, size_t smem, cudaStream_t s, const CUtensorMap& corpus, const CUtensorMap& queries,
                       const TcParams& p) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -60,7 +60,7 @@ cudaError_t tc_launch(int ctas, size_t smem, cudaStream_t s, const CUtensorMap& 
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // the kernel calls grid_dep_wait() itself
-    at[1].val.programmaticStreamSerializationAllowed = g_pdl_enabled ? 1 : 0;
+    at[1].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = at;
     cfg.numAttrs = 2;
     return cudaLaunchKernelEx(&cfg, gemm_topk_kernel<PREPASS, PAIR>, corpus, queries, p);
@@ -90,6 +90,7 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
     TensorPathState& tc = idx->tc;
     const int cap = list_capacity(k);
     const int kblocks = idx->dim / kTcKBlock;
+    const bool pdl = idx->opt_pdl != 0;
     if (!tc.corpus_map_valid) {
         if ((rc = tc_encode_rows(idx, &tc.corpus_map, idx->rows, (uint64_t)idx->n, kTcRowsPerCta)) != B2S_OK) return rc;
         if ((rc = tc_encode_rows(idx, &tc.corpus_map_full, idx->rows, (uint64_t)idx->n, kTcTileRows)) != B2S_OK) return rc;
@@ -197,10 +198,10 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
             pp.policy = ptx::kEvictNormal;
             pp.gmax = reinterpret_cast<float*>(idx->ws_gmax.p);
             pp.groups = groups;
-            if (pair_mode) CUDA_TRY((tc_launch<true, true>(ctas, L.total + 1024, s, corpus_map, qmap, pp)));
-            else CUDA_TRY((tc_launch<true, false>(ctas, L.total + 1024, s, corpus_map, qmap, pp)));
+            if (pair_mode) CUDA_TRY((tc_launch<true, true>(pdl, ctas, L.total + 1024, s, corpus_map, qmap, pp)));
+            else CUDA_TRY((tc_launch<true, false>(pdl, ctas, L.total + 1024, s, corpus_map, qmap, pp)));
             const int sel_smem = (size_t)groups * 4 <= 40 * 1024 ? groups * 4 : 0;   // images staged in shared memory
-            CUDA_TRY(launch_pdl(seed_select_kernel, dim3((unsigned)nq_pad), dim3(kSeedThreads), (size_t)sel_smem, s,
+            CUDA_TRY(launch_pdl(pdl, seed_select_kernel, dim3((unsigned)nq_pad), dim3(kSeedThreads), (size_t)sel_smem, s,
                                 (const float*)pp.gmax, groups, k, reinterpret_cast<u64*>(idx->ws_seed.p),
                                 shared_thr ? reinterpret_cast<uint2*>(idx->ws_hcfg.p) : (uint2*)nullptr, sel_smem ? 1 : 0));
             idx->stats.kernel_launches += 2;
@@ -219,8 +220,8 @@ int search_tensor(b2s_index* idx, const void* queries, int q_dtype, int64_t nq, 
                                     : tc_pick_chunk(tiles_all, 1, pairs, 8, 32);
         p.num_chunks = (tiles_all + p.chunk_tiles - 1) / p.chunk_tiles;
         if (idx->time_this && c0 == 0) cudaEventRecord(idx->ev[1], s);
-        if (pair_mode) CUDA_TRY((tc_launch<false, true>(ctas, L.total + 1024, s, corpus_map, qmap, p)));
-        else CUDA_TRY((tc_launch<false, false>(ctas, L.total + 1024, s, corpus_map, qmap, p)));
+        if (pair_mode) CUDA_TRY((tc_launch<false, true>(pdl, ctas, L.total + 1024, s, corpus_map, qmap, p)));
+        else CUDA_TRY((tc_launch<false, false>(pdl, ctas, L.total + 1024, s, corpus_map, qmap, p)));
         idx->stats.kernel_launches++;
         idx->stats.passes += qblocks;
         if (idx->time_this && c0 == 0) cudaEventRecord(idx->ev[2], s);

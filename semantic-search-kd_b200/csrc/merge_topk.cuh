@@ -58,6 +58,38 @@ __device__ __forceinline__ void block_sort_desc(u64* buf, int m, int tid) {
     bitonic_sort_desc(buf, n, tid, NT, BlockSync());
 }
 
+// Merge G runs of k_in (score, id) candidates each, every run sorted by (score desc, id asc) and run r
+// holding smaller ids than run r+1 (rank order): the global position of candidate (r, i) is i plus, for
+// every other run, the number of its entries that precede (r, i) -- one binary search per run, straight
+// from global memory, so G * k_in is not bounded by the shared-memory sort buffer (8 ranks x k = 2048).
+// Padding entries (-FLT_MAX, -1) sort last and are copied through like any other entry.
+template <int NT, typename ScoreAt, typename IdAt>
+__device__ __forceinline__ void merge_runs_bsearch(int G, int k_in, int k_out, ScoreAt score_at, IdAt id_at,
+                                                   float* out_scores, long long* out_ids) {
+    const int total = G * k_in;
+    for (int e = threadIdx.x; e < total; e += NT) {
+        const int r = e / k_in, i = e - r * k_in;
+        const float s = score_at(r, i);
+        int rank = i;
+        for (int r2 = 0; r2 < G && rank < k_out; ++r2) {
+            if (r2 == r) continue;
+            int lo = 0, hi = k_in;   // first entry of run r2 that does NOT precede (s, r)
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const float s2 = score_at(r2, mid);
+                const bool prec = (s2 > s) || (s2 == s && r2 < r);
+                if (prec) lo = mid + 1;
+                else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < k_out) {
+            out_scores[rank] = s;
+            out_ids[rank] = id_at(r, i);
+        }
+    }
+}
+
 constexpr int kMergeMaxLists = 512;   // candidate lists per query (CTAs of the producing kernel)
 constexpr int kMergeFastCap = 512;    // survivors the rank-sort fast path can hold
 
@@ -389,7 +421,15 @@ __global__ void __launch_bounds__(kMergeThreads) merge_pairs_kernel(const MergeP
     __shared__ u64 buf[kMergeSortCap];
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
-    const int total = p.g * p.k_in;  // host guarantees total <= kMergeSortCap
+    const int total = p.g * p.k_in;
+    if (total > kMergeSortCap) {
+        const size_t qoff = (size_t)q * p.k_in;
+        merge_runs_bsearch<kMergeThreads>(
+            p.g, p.k_in, p.k, [&](int g, int j) { return p.in_scores[(size_t)g * p.g_stride_scores + qoff + j]; },
+            [&](int g, int j) { return p.in_ids[(size_t)g * p.g_stride_ids + qoff + j]; },
+            p.out_scores + (size_t)q * p.k, p.out_ids + (size_t)q * p.k);
+        return;
+    }
     for (int i = tid; i < total; i += kMergeThreads) {
         const int g = i / p.k_in, j = i - g * p.k_in;
         const size_t off = (size_t)q * p.k_in + j;

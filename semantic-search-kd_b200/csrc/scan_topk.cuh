@@ -5,15 +5,30 @@
 // /root/reference/src/kd/eval.py:75,86.
 //
 // HBM-bound: one pass over the bf16 corpus (dim*2 bytes per row), nothing written back but the
-// per-CTA candidate lists (<= capacity keys per query).  Mapping: a HALF-WARP owns one row; lane
-// l (0..15) reads the 16-byte chunks l, l+16, l+32, ... of that row with 128-bit
-// ld.global.nc.L1::no_allocate loads, so a warp instruction covers two rows x 256 contiguous bytes.
-// Each warp keeps U row-pairs (2U rows, U*CPL independent 16-byte loads per lane) in flight per
-// iteration.  bf16 -> fp32 is a shift / mask, products are accumulated in fp32 against the query
-// held in registers as fp32 (the query is NOT rounded to bf16 on this path), a 4-step xor-shuffle
-// finishes the dot product inside the half-warp.  Scores that reach the CTA's current k-th best
-// are appended to the shared-memory candidate list (select.cuh); everything else is dropped in
-// registers, so the [N] score vector never exists in memory.
+// candidates (<= k keys per query).  Mapping: a HALF-WARP owns one row; lane l (0..15) reads the
+// 16-byte chunks l, l+16, l+32, ... of that row with 128-bit ld.global.nc.L1::no_allocate loads, so a
+// warp instruction covers two rows x 256 contiguous bytes.  Each warp keeps U row-pairs (2U rows,
+// U*CPL independent 16-byte loads per lane) in flight per iteration.  bf16 -> fp32 is a shift / mask,
+// products are accumulated in fp32 against the query held in registers as fp32 (the query is NOT
+// rounded to bf16 on this path), a 4-step xor-shuffle finishes the dot product inside the half-warp.
+// Scores that reach the current k-th best are kept, everything else is dropped in registers, so the
+// [N] score vector never exists in memory.
+//
+// Work distribution: the first S*G units (G = grid, a unit = 8 warps x 2U rows = 48 KB at dim 384) are
+// dealt statically, CTA b takes units b, b + G, ... so that the whole grid reads one compact ~14 MB
+// window at any moment; the LAST few units per CTA are handed out dynamically, 2U rows per atomic
+// ticket (fetched one iteration ahead), so every warp of the GPU finishes within one iteration
+// (~2 us) of every other -- the end of a 0.12 ms shard scan at 8 GPUs is not a ragged tail.
+//
+// Two ways of keeping the survivors (select_mode):
+//   0  per-CTA shared-memory lists (select.cuh), published sorted; the last CTA to finish (or a
+//      separate merge kernel) merges the G lists.  Any k <= 2048.
+//   1  "cascade" (k <= 16, large shards): after a short phase A with the shared-memory lists every CTA
+//      offers its local top-k to ONE global array of k sorted slots per query (lock-free insertion:
+//      a chain of 64-bit atomicMax that carries the smaller key downwards), and from then on the
+//      slots' k-th key IS every CTA's threshold: a row that beats it is inserted straight away
+//      (~k ln(1/phase A fraction) insertions per query over the whole GPU).  When the scan ends the
+//      answer already sits sorted in the slots: the last CTA only reads k keys -- no merge.
 #pragma once
 #include "exchange.cuh"
 #include "merge_topk.cuh"
@@ -24,6 +39,12 @@ namespace b2s {
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kScanInlineFloats = 768;   // queries of a host call travel inside the kernel parameters (<= 3 KB)
+constexpr int kScanMaxNQ = 4;            // queries one launch holds in registers
+constexpr int kCascadeMaxK = 16;         // slots per query of the cascade select
+constexpr int kWorkCounterStride = 32;   // words between the dynamic tail's ticket counters (one 128-byte line each)
+constexpr int kTraceWords = 16;          // header of the trace buffer, then kTraceArrays arrays of kTraceStride per-CTA stamps:
+constexpr int kTraceStride = 512;        //   0 start, 1 scan end, 2 transition begin, 3 transition end, 4 static part end, 5 SM id
+constexpr int kTraceArrays = 6;
 
 struct ScanParams {
     const uint4* corpus;   // bf16 rows, row-major, dim*2 bytes each (16-byte aligned)
@@ -38,16 +59,41 @@ struct ScanParams {
     u64* lists;            // out [gridDim.x, nq_lists, cap]
     int* counts;           // out [gridDim.x, nq_lists]
     int nq_lists;          // stride (in queries) of the list arrays
-    int pdl_late_wait;     // 1: nothing this kernel READS is produced by the preceding kernel of the
-                           // stream, so the PDL wait is deferred to just before the list write-out
-                           // (the scan of query i+1 then overlaps the merge of query i)
-    // Fused tail: the LAST CTA to publish its lists (ticket from *done_counter) merges all lists of
-    // the launch's queries itself -- no separate merge kernel, no kernel boundary.  1 = write the
-    // final top-k (mp.out_*); 2 = sharded search: push to the peers, wait, merge (ex).
+    int pdl_late_wait;     // 1: the caller guarantees that the query buffer was complete before the PREVIOUS
+                           // kernel of the stream was enqueued (B2S_SEARCH_STABLE_QUERIES), so nothing this
+                           // kernel reads early is produced by its predecessor: the PDL wait is deferred to
+                           // the first point where state shared with the predecessor is touched (cascade:
+                           // the phase A -> B transition; lists: before the dynamic tail / the write-out)
+    // Fused tail: the LAST CTA to finish (ticket from *done_counter) produces the final top-k itself -- no
+    // separate merge kernel, no kernel boundary.  1 = write the final top-k (mp.out_*); 2 = sharded
+    // search: push to the peers, wait, merge (ex).
     int fused_tail;
     unsigned* done_counter;   // zero before the launch; the last CTA resets it
     MergeParams mp;
     ExchangeArgs ex;
+    // dynamic tail: rows [dyn_begin, n_rows) are handed out 2U rows per ticket (dyn_begin == n_rows: all static)
+    long long dyn_begin;
+    unsigned* work_counter;   // kScanWarps counters, kWorkCounterStride words apart (one per region of the dynamic
+                              // tail: 2400 warps on one address would be bound by L2 atomic throughput); zero before
+                              // the launch, the last CTA resets them
+    // cascade select
+    int select_mode;          // 0 lists, 1 cascade
+    int phase_a_iters;        // iterations every warp runs against the shared-memory lists first ...
+    int phase_a_stagger;      // ... plus blockIdx % phase_a_stagger: the CTAs reach the slots a few at a time, so
+                              // that the peek of a late CTA already sees (and is filtered by) the early ones' keys
+    u64* gslots;              // [kScanMaxNQ][kCascadeMaxK] running global top-k, zero before the launch
+    int transition_mode;      // 1 (default): the CTA waits for the bound, not for the insertion chain; 0 / 2: A/B variants
+    int peek_every;           // phase B: warp 0 re-reads the slots' k-th key every this many iterations (0 = never)
+    // L2 prefetch of this warp's first iterations, issued BEFORE the PDL wait: the corpus is immutable
+    // while searches are in flight, so the idle DRAM time of the predecessor's tail is put to use
+    int prefetch_iters;
+    // 1 (default): the dependent launch is triggered at the START of the kernel, so the next kernel of the stream
+    // is already queued behind this one and its CTAs take over SM slots the moment this grid's CTAs retire (no
+    // launch latency after the last CTA's scan).  Safe: every CTA of this grid is resident by then, and a
+    // dependent kernel touches state shared with this one only behind its own griddepcontrol.wait, which returns
+    // when this grid has completed.  0: trigger after the scan (A/B switch).
+    int early_trigger;
+    unsigned long long* trace;   // optional (option "trace"): globaltimer stamps, see kTraceWords
     // Host-buffer searches of 1-2 queries: the query rides in the kernel parameters (constant bank) -- no
     // staging copy, no H2D operation in front of the kernel.
     int use_inline;
@@ -62,6 +108,17 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
     return r;
 }
 
+// pinned in program order among the (volatile) corpus loads: issued where it is written, consumed an iteration later
+__device__ __forceinline__ u64 ldcg_pinned_u64(const u64* p) {
+    u64 v;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ float dot8(const uint4& w, const float* q, float acc) {
     acc = fmaf(__uint_as_float(w.x << 16), q[0], acc);
     acc = fmaf(__uint_as_float(w.x & 0xffff0000u), q[1], acc);
@@ -72,6 +129,53 @@ __device__ __forceinline__ float dot8(const uint4& w, const float* q, float acc)
     acc = fmaf(__uint_as_float(w.w << 16), q[6], acc);
     acc = fmaf(__uint_as_float(w.w & 0xffff0000u), q[7], acc);
     return acc;
+}
+
+// if (pred) old = atomicMax(addr, v); else old = v;   (no branch: see the note on lane-uniform control flow in select.cuh)
+__device__ __forceinline__ u64 atom_max_u64_if(u64* addr, u64 v, bool pred) {
+    u64 old = v;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.u32 p, %3, 0;\n\t"
+        "@p atom.global.max.u64 %0, [%1], %2;\n\t"
+        "}\n"
+        : "+l"(old)
+        : "l"(addr), "l"(v), "r"((uint32_t)pred)
+        : "memory");
+    return old;
+}
+
+// Lock-free insertion of (unique) keys into k global slots kept sorted descending -- warp-collective, every
+// lane may bring one key (`active`), control flow is warp-uniform throughout.  The peek finds, per lane, the
+// first slot below its key (slots only ever grow, so the slots above it stay above it for ever); from there
+// atomicMax leaves the larger key in the slot and the smaller one is carried to the next slot.  At quiescence
+// slot j holds the (j+1)-th largest key ever offered, whatever the interleaving of lanes, warps and CTAs.
+__device__ __forceinline__ void cascade_insert_warp(u64* slots, int k, bool active, u64 key) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const ulonglong2* sv = reinterpret_cast<const ulonglong2*>(slots);
+    ulonglong2 v[kCascadeMaxK / 2];
+#pragma unroll
+    for (int i = 0; i < kCascadeMaxK / 2; ++i) v[i] = __ldcg(sv + i);
+    int j0 = k;   // first slot this lane's key has to visit
+#pragma unroll
+    for (int i = kCascadeMaxK / 2 - 1; i >= 0; --i) {
+        j0 = (2 * i + 1 < k && v[i].y < key) ? 2 * i + 1 : j0;
+        j0 = (2 * i < k && v[i].x < key) ? 2 * i : j0;
+    }
+    active = active && j0 < k;
+    j0 = active ? j0 : k;
+    int jmin = j0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) jmin = min(jmin, __shfl_xor_sync(kFull, jmin, off));
+    for (int j = jmin; j < k; ++j) {   // uniform bounds
+        const bool doit = active && j >= j0;
+        const u64 old = atom_max_u64_if(slots + j, key, doit);
+        const bool displaced = doit && old < key;
+        active = active && !(displaced && old == 0ull);   // an empty slot took it: done
+        key = displaced ? old : key;                        // carry the smaller key down
+        if (!__any_sync(kFull, active)) break;              // uniform
+    }
 }
 
 // CPL = 16-byte chunks per lane = dim / 128; NQ = queries held in registers; U = row pairs in flight.
@@ -93,8 +197,34 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
     const int hl = lane & 15;
     constexpr int kChunksPerRow = CPL * 16;  // uint4 per row
     constexpr int kRowsPerIter = 2 * U;
+    constexpr long long kUnitRows = (long long)kScanWarps * kRowsPerIter;
+    constexpr unsigned kFull = 0xffffffffu;
 
+    const long long row_end = p.n_rows;
+    const long long last_row = p.n_rows - 1;
+    const long long static_end = p.dyn_begin;     // == row_end when nothing is dealt dynamically
+    const bool dynamic = static_end < row_end;
+    const bool cascade = p.select_mode == 1;
+    const long long step = kUnitRows * (long long)gridDim.x * p.unit_stride;
+    long long base = kUnitRows * (long long)blockIdx.x * p.unit_stride + (long long)warp * kRowsPerIter;
+
+    // L2 prefetch before the PDL wait (lane i: this warp's i-th static iteration)
+    if (lane < p.prefetch_iters) {
+        const long long b = base + (long long)lane * step;
+        if (b + kRowsPerIter <= static_end)
+            prefetch_l2_bulk(p.corpus + b * kChunksPerRow, (uint32_t)(kRowsPerIter * kChunksPerRow * 16));
+    }
+    if (p.early_trigger) grid_dep_launch();
     if (!p.pdl_late_wait) grid_dep_wait();
+    auto stamp = [&](int which) {
+        if (p.trace != nullptr && tid == 0) p.trace[kTraceWords + which * kTraceStride + blockIdx.x] = globaltimer_ns();
+    };
+    stamp(0);
+    if (p.trace != nullptr && tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.trace[kTraceWords + 5 * kTraceStride + blockIdx.x] = smid;
+    }
     if (tid < NQ) {
         u64 seed = 0ull;
         if (p.seed_keys != nullptr && tid < p.nq_valid) seed = p.seed_keys[p.q_begin + tid];
@@ -119,17 +249,10 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
     }
     __syncthreads();
 
-    // Grid-stride schedule: a "unit" is kScanWarps * 2U consecutive rows (48 KB at dim 384); CTA b
-    // takes units b, b + G, b + 2G, ...  At any moment the whole grid therefore reads one compact
-    // window of G units (~14 MB), which keeps DRAM pages and the 2 MB-page TLB hot -- unlike a
-    // contiguous per-CTA partition, where G distant regions stream at once.
-    const long long row_end = p.n_rows;
-    const long long last_row = p.n_rows - 1;
-
-    // Rare path, kept out of line of the hot loop: pick the row this lane speaks for (lane hl < U
-    // of each half-warp owns row base + 2*hl + half), re-test it and append under the list lock.
-    auto offer = [&](long long base, const float (&acc)[NQ][U]) {
-        const long long myrow = base + 2 * hl + half;
+    // Rare path, kept out of line of the hot loop: pick the row this lane speaks for (lane hl < U of each
+    // half-warp owns row base + 2*hl + half) and re-test it.  List mode: append under the list lock.
+    auto offer_list = [&](long long b, const float (&acc)[NQ][U]) {
+        const long long myrow = b + 2 * hl + half;
         const bool row_ok = (hl < U) && (myrow < row_end);
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
@@ -137,22 +260,50 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
 #pragma unroll
             for (int i = 1; i < U; ++i) s = (hl == i) ? acc[q][i] : s;
             const bool pass = row_ok && (s >= *(volatile float*)&s_thr[q]);
-            if (__any_sync(0xffffffffu, pass)) {
+            if (__any_sync(kFull, pass)) {
                 list_append_warp(list_of(q), entries + (size_t)q * p.cap, p.cap, p.k, pass,
                                  make_key(s, (uint32_t)myrow), lane);
             }
         }
     };
+    // every lane stores the same values: no lane predicate, no branch
+    auto adopt_bound = [&](int q, u64 kth) {
+        if (kth > *(volatile u64*)&s_thr_key[q]) {   // uniform (all lanes hold the same kth)
+            *(volatile u64*)&s_thr_key[q] = kth;
+            *(volatile float*)&s_thr[q] = key_score(kth);
+        }
+    };
+    // Cascade mode (phase B): straight into the global slots, then pick up the slots' new k-th key.
+    auto offer_global = [&](long long b, const float (&acc)[NQ][U]) {
+        const long long myrow = b + 2 * hl + half;
+        const bool row_ok = (hl < U) && (myrow < row_end);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            float s = acc[q][0];
+#pragma unroll
+            for (int i = 1; i < U; ++i) s = (hl == i) ? acc[q][i] : s;
+            const bool pass = row_ok && (s >= *(volatile float*)&s_thr[q]);
+            if (__any_sync(kFull, pass)) {
+                u64* slots = p.gslots + q * kCascadeMaxK;
+                const u64 key = make_key(s, (uint32_t)myrow);
+                const bool ins = pass && key > *(volatile u64*)&s_thr_key[q];
+                cascade_insert_warp(slots, p.k, ins, key);
+                if (p.trace != nullptr) {   // diagnostics: warp-level offers / keys sent to the slots in phase B
+                    const unsigned m = __ballot_sync(kFull, ins);
+                    if (lane == 0) {
+                        atomicAdd(p.trace + 8, 1ull);
+                        atomicAdd(p.trace + 9, (unsigned long long)__popc(m));
+                    }
+                }
+                __syncwarp();
+                adopt_bound(q, __ldcg(slots + p.k - 1));
+                __syncwarp();
+            }
+        }
+    };
 
-    constexpr long long kUnitRows = (long long)kScanWarps * kRowsPerIter;
-    const long long step = kUnitRows * (long long)gridDim.x * p.unit_stride;
-    long long base = kUnitRows * (long long)blockIdx.x * p.unit_stride + (long long)warp * kRowsPerIter;
-    // lane's pointer to chunk hl of row (base + half); advanced by `step` rows per iteration
-    const uint4* rp = p.corpus + (base + half) * kChunksPerRow + hl;
-    const long long rp_step = step * kChunksPerRow;
-
-    // ---- hot loop: all 2U rows of the unit exist; no clamps, no per-lane selects ----------------
-    for (; base + kRowsPerIter <= row_end; base += step, rp += rp_step) {
+    // One iteration on 2U full rows: rp = this lane's pointer to chunk hl of row (b + half).
+    auto scan_rows = [&](const uint4* rp, long long b, auto&& offer) {
         uint4 w[U][CPL];
 #pragma unroll
         for (int i = 0; i < U; ++i)
@@ -173,7 +324,7 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
 #pragma unroll
             for (int q = 0; q < NQ; ++q)
 #pragma unroll
-                for (int i = 0; i < U; ++i) acc[q][i] += __shfl_xor_sync(0xffffffffu, acc[q][i], off);
+                for (int i = 0; i < U; ++i) acc[q][i] += __shfl_xor_sync(kFull, acc[q][i], off);
         // after the butterfly every lane of a half-warp holds all U sums of its half
         bool hot = false;
 #pragma unroll
@@ -182,16 +333,15 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
 #pragma unroll
             for (int i = 0; i < U; ++i) hot = hot || (acc[q][i] >= t);
         }
-        if (__any_sync(0xffffffffu, hot)) offer(base, acc);
+        if (__any_sync(kFull, hot)) offer(b, acc);
         __syncwarp();
-    }
-
-    // ---- tail: the (at most one) partial unit of this warp, loads clamped to the last row --------
-    if (base < row_end) {
+    };
+    // The (at most one) partial group of rows at the end of the shard: loads clamped to the last row.
+    auto scan_rows_clamped = [&](long long b, auto&& offer) {
         float acc[NQ][U];
 #pragma unroll
         for (int i = 0; i < U; ++i) {
-            long long r = base + 2 * i + half;
+            long long r = b + 2 * i + half;
             if (r > last_row) r = last_row;
             const uint4* tp = p.corpus + r * kChunksPerRow + hl;
             uint4 w[CPL];
@@ -210,28 +360,139 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
 #pragma unroll
             for (int q = 0; q < NQ; ++q)
 #pragma unroll
-                for (int i = 0; i < U; ++i) acc[q][i] += __shfl_xor_sync(0xffffffffu, acc[q][i], off);
-        offer(base, acc);
+                for (int i = 0; i < U; ++i) acc[q][i] += __shfl_xor_sync(kFull, acc[q][i], off);
+        offer(b, acc);
         __syncwarp();
+    };
+    // Cascade phase B: warp 0 re-reads the slots' k-th key once per iteration (other CTAs raise it); the
+    // load flies during the iteration's corpus loads.
+    // (all lanes load the same word -- query `peek_q`, rotating -- and later store the same values: uniform)
+    int peek_in = p.peek_every;   // iterations until warp 0 peeks again (0: never -- inserts refresh the bound anyway)
+    int peek_q = 0, peeked_q = 0;
+    auto bound_peek = [&]() -> u64 {
+        u64 g = 0ull;
+        if (warp == 0 && p.peek_every > 0 && --peek_in == 0) {   // uniform
+            peek_in = p.peek_every;
+            peeked_q = peek_q;
+            g = ldcg_pinned_u64(p.gslots + peek_q * kCascadeMaxK + p.k - 1);
+            peek_q = peek_q + 1 < p.nq_valid ? peek_q + 1 : 0;
+        }
+        return g;
+    };
+    auto bound_apply = [&](u64 g) {
+        if (g != 0ull) adopt_bound(peeked_q, g);   // uniform: every lane of warp 0 holds the same g
+    };
+
+    // lane's pointer to chunk hl of row (base + half); advanced by `step` rows per iteration
+    const uint4* rp = p.corpus + (base + half) * kChunksPerRow + hl;
+    const long long rp_step = step * kChunksPerRow;
+
+    // ---- static part, against the shared-memory lists (cascade: only the first phase_a_iters) ------
+    {
+        int it = 0;
+        const int it_end = cascade ? p.phase_a_iters + (int)(blockIdx.x % (unsigned)p.phase_a_stagger) : 0x7fffffff;
+        for (; base + kRowsPerIter <= static_end && it < it_end; base += step, rp += rp_step, ++it)
+            scan_rows(rp, base, offer_list);
+    }
+    u64 g_bound = 0ull;   // cascade: the slots' k-th key as peeked one iteration ago (warp 0, lane = query)
+    if (cascade) {
+        // ---- phase A -> B: warp q sorts query q's local list and adopts the better of its k-th key and the
+        // global slots' k-th key as the CTA's bound (one L2 round trip); after the second barrier the other
+        // warps go on against that bound while warp q alone walks the chain of atomics that offers the local
+        // top-k to the slots -- the CTA stalls for a load, not for the chain.
+        __syncthreads();                        // nobody appends to the shared-memory lists any more
+        stamp(2);
+        if (p.pdl_late_wait) grid_dep_wait();   // the predecessor has reset the slots / counters and is gone
+        int c_mine = 0;
+        if (warp < p.nq_valid) {                // warp-uniform
+            c_mine = list_compact_warp(list_of(warp), entries + (size_t)warp * p.cap, p.cap, p.k, lane);
+            if (p.transition_mode == 0)         // (A/B switch: the whole CTA waits for the chain)
+                cascade_insert_warp(p.gslots + warp * kCascadeMaxK, p.k, lane < c_mine,
+                                    entries[(size_t)warp * p.cap + (lane < c_mine ? lane : 0)]);
+            __syncwarp();
+            adopt_bound(warp, __ldcg(p.gslots + warp * kCascadeMaxK + p.k - 1));   // every lane: same word, same stores
+            __syncwarp();
+        }
+        if (p.transition_mode != 2) __syncthreads();
+        if (warp < p.nq_valid) {
+            const int q = warp;
+            u64* slots = p.gslots + q * kCascadeMaxK;
+            if (p.transition_mode != 0)
+                cascade_insert_warp(slots, p.k, lane < c_mine, entries[(size_t)q * p.cap + (lane < c_mine ? lane : 0)]);
+            if (p.trace != nullptr && lane == 0) atomicAdd(p.trace + 10, (unsigned long long)c_mine);
+            __syncwarp();
+            adopt_bound(q, __ldcg(slots + p.k - 1));
+            __syncwarp();
+            if (warp == 0) stamp(3);
+        }
+        for (; base + kRowsPerIter <= static_end; base += step, rp += rp_step) {
+            const u64 g = bound_peek();     // lands during this iteration's loads, applied at the start of the next
+            bound_apply(g_bound);
+            scan_rows(rp, base, offer_global);
+            g_bound = g;
+        }
+    } else {
+        // static tail (only when nothing is dealt dynamically): this warp's partial group, if any
+        if (!dynamic && base < row_end) scan_rows_clamped(base, offer_list);
+        if (p.pdl_late_wait && dynamic) grid_dep_wait();   // the predecessor has reset the work counter
+    }
+
+    if (p.trace != nullptr && warp == 0 && lane == 0) p.trace[kTraceWords + 4 * kTraceStride + blockIdx.x] = globaltimer_ns();
+    // ---- dynamic tail: 2U rows per ticket, the next ticket is fetched before the current rows are read.  The
+    // chunks are split into kScanWarps regions with a counter each; a warp starts in the region of its own
+    // index and moves on to the next one when a region is drained.
+    if (dynamic) {
+        const unsigned n_chunks = (unsigned)((row_end - static_end + kRowsPerIter - 1) / kRowsPerIter);
+        const unsigned per_region = (n_chunks + kScanWarps - 1) / kScanWarps;
+        for (int r = 0; r < kScanWarps; ++r) {
+            const unsigned region = (unsigned)((warp + r) % kScanWarps);
+            const unsigned c0 = region * per_region;
+            if (c0 >= n_chunks) continue;
+            const unsigned cn = min(per_region, n_chunks - c0);
+            unsigned* ctr = p.work_counter + region * kWorkCounterStride;
+            unsigned nxt = 0u;
+            if (lane == 0) nxt = atomicAdd(ctr, 1u);
+            nxt = __shfl_sync(kFull, nxt, 0);
+            while (nxt < cn) {
+                const long long b = static_end + (long long)(c0 + nxt) * kRowsPerIter;
+                unsigned t = 0u;
+                if (lane == 0) t = atomicAdd(ctr, 1u);
+                const uint4* dp = p.corpus + (b + half) * kChunksPerRow + hl;
+                if (cascade) {
+                    const u64 g = bound_peek();
+                    bound_apply(g_bound);
+                    if (b + kRowsPerIter <= row_end) scan_rows(dp, b, offer_global);
+                    else scan_rows_clamped(b, offer_global);
+                    g_bound = g;
+                } else {
+                    if (b + kRowsPerIter <= row_end) scan_rows(dp, b, offer_list);
+                    else scan_rows_clamped(b, offer_list);
+                }
+                nxt = __shfl_sync(kFull, t, 0);
+            }
+        }
     }
     __syncthreads();
-    grid_dep_launch();                          // the merge kernel may be scheduled: its launch latency hides here
-    if (p.pdl_late_wait) grid_dep_wait();       // the previous call's merge has finished reading the lists
+    stamp(1);
+    if (!p.early_trigger) grid_dep_launch();   // (A/B) the next kernel may be scheduled from here on
 
-    // final: leave exactly min(count, k) best keys per query, SORTED descending (the merge kernel
-    // relies on it: a list's first key is its maximum), then publish
-    for (int q = warp; q < NQ; q += kScanWarps)
-        list_compact_warp(list_of(q), entries + (size_t)q * p.cap, p.cap, p.k, lane);
-    __syncthreads();
-    for (int q = 0; q < p.nq_valid; ++q) {
-        const int c = s_count[q];
-        u64* dst = p.lists + ((size_t)blockIdx.x * p.nq_lists + (p.q_begin + q)) * p.cap;
-        for (int i = tid; i < c; i += kScanThreads) dst[i] = entries[(size_t)q * p.cap + i];
-        if (tid == 0) p.counts[(size_t)blockIdx.x * p.nq_lists + (p.q_begin + q)] = c;
+    if (!cascade) {
+        if (p.pdl_late_wait && !dynamic) grid_dep_wait();   // the previous call's merge has finished reading the lists
+        // final: leave exactly min(count, k) best keys per query, SORTED descending (the merge relies on
+        // it: a list's first key is its maximum), then publish
+        for (int q = warp; q < NQ; q += kScanWarps)
+            list_compact_warp(list_of(q), entries + (size_t)q * p.cap, p.cap, p.k, lane);
+        __syncthreads();
+        for (int q = 0; q < p.nq_valid; ++q) {
+            const int c = s_count[q];
+            u64* dst = p.lists + ((size_t)blockIdx.x * p.nq_lists + (p.q_begin + q)) * p.cap;
+            for (int i = tid; i < c; i += kScanThreads) dst[i] = entries[(size_t)q * p.cap + i];
+            if (tid == 0) p.counts[(size_t)blockIdx.x * p.nq_lists + (p.q_begin + q)] = c;
+        }
     }
-    if (p.fused_tail == 0) return;
+    if (p.fused_tail == 0 && !dynamic) return;
 
-    // ---- fused tail: last CTA done merges (threadfence reduction pattern) ------------------------
+    // ---- last CTA done (threadfence reduction pattern): resets the counters, runs the fused tail -----
     __shared__ MergeSmem sm;
     __shared__ int s_last;
     __threadfence();
@@ -243,11 +504,36 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (tid == 0) *p.done_counter = 0u;   // ready for the next launch (stream-ordered after this kernel)
+    if (tid == 0) {
+        *p.done_counter = 0u;   // ready for the next launch (stream-ordered after this kernel)
+    }
+    if (dynamic && tid < kScanWarps) p.work_counter[tid * kWorkCounterStride] = 0u;
+    if (p.fused_tail == 0) return;
+    unsigned long long* tr = (p.trace != nullptr && tid == 0) ? p.trace : nullptr;
+    if (tr) {
+        tr[0] = gridDim.x;
+        tr[1] = globaltimer_ns();
+        tr[11] = tr[8], tr[12] = tr[9], tr[13] = tr[10];   // this launch's diagnostics counters
+        tr[8] = tr[9] = tr[10] = 0ull;
+    }
     for (int q = 0; q < p.nq_valid; ++q) {
         const int lq = p.q_begin + q;     // list / output index of this query inside the call
-        const int m_sorted = merge_lists_sorted<kScanThreads>(p.mp, lq, sm);
-        const int kk = m_sorted < p.mp.k ? m_sorted : p.mp.k;
+        int kk;
+        if (cascade) {
+            u64* slots = p.gslots + q * kCascadeMaxK;
+            if (tid < kCascadeMaxK) {
+                const u64 key = tid < p.k ? __ldcg(slots + tid) : 0ull;
+                sm.buf[tid] = key;
+                slots[tid] = 0ull;            // ready for the next launch
+            }
+            __syncthreads();
+            kk = 0;
+            for (int i = 0; i < p.k; ++i) kk += sm.buf[i] != 0ull;   // sorted: the non-empty slots are a prefix
+        } else {
+            const int m_sorted = merge_lists_sorted<kScanThreads>(p.mp, lq, sm);
+            kk = m_sorted < p.mp.k ? m_sorted : p.mp.k;
+        }
+        if (tr) tr[2] = globaltimer_ns();
         if (p.fused_tail == 1) {
             for (int i = tid; i < p.mp.k; i += kScanThreads) {
                 float s = -FLT_MAX;
@@ -262,10 +548,11 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
             }
         } else {
             const long long gq = (long long)p.ex.q_offset + lq;
-            exchange_fused<kScanThreads>(p.ex, p.mp, sm.buf, kk, gq);
+            exchange_fused<kScanThreads>(p.ex, p.mp, sm.buf, kk, gq, tr);
         }
         __syncthreads();
     }
+    if (tr) tr[5] = globaltimer_ns();
 }
 
 }  // namespace b2s

@@ -75,6 +75,13 @@ __device__ __forceinline__ void st_u64_if(u64* ptr, u64 v, bool pred) {
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// nanoseconds of the GPU-wide timer (comparable across SMs; ~32 ns granularity): option "trace" stamps
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // In-place bitonic sort, DESCENDING, of a[0..n) (n a power of two, n/2 a multiple of nthreads)
 // by `nthreads` cooperating threads with ids tid in [0, nthreads).  `sync` is __syncwarp or
 // __syncthreads.  Compare-exchange is select + unconditional stores.

@@ -46,6 +46,18 @@ def write_flat_ip(path: Path, blocks: Iterable[np.ndarray], ntotal: int, dim: in
     return written
 
 
+def read_header(path: Path) -> Tuple[int, int, int]:
+    """(d, ntotal, metric_type) of an IndexFlat file; ValueError for anything else."""
+    with open(Path(path), "rb") as f:
+        head = f.read(_HEADER.size)
+    if len(head) < _HEADER.size:
+        raise ValueError(f"{path}: truncated FAISS header")
+    fourcc, d, ntotal, _d1, _d2, _trained, metric = _HEADER.unpack(head)
+    if fourcc not in (FOURCC_IP, FOURCC_L2):
+        raise ValueError(f"{path}: unsupported FAISS index type {fourcc!r}")
+    return int(d), int(ntotal), int(metric)
+
+
 def read_flat(path: Path) -> Tuple[np.ndarray, int]:
     """Memory-map the vectors of an IndexFlat file.  Returns (fp32 [ntotal, d] memmap, metric)."""
     path = Path(path)

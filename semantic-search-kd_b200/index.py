@@ -36,6 +36,7 @@ except Exception:  # pragma: no cover
 ArrayLike = Union[np.ndarray, "torch.Tensor"]
 _SIDE_CAR = "rows.bf16"
 _SIDE_META = "b200_meta.json"
+_METRIC_ALIASES = {"ip": "inner_product", "dot": "inner_product"}
 
 
 def _check(rc: int, what: str) -> None:
@@ -266,7 +267,15 @@ class FlatIPIndex:
                 json.dump(self.doc_texts, f)
 
     def load(self, index_dir: Path, block_rows: int = 1 << 18) -> "FlatIPIndex":
-        """``src/serve/app.py:430-433``: restore rows and ``doc_ids`` from an index directory."""
+        """``src/serve/app.py:430-433``: restore rows and ``doc_ids`` from an index directory.
+
+        Rows come back VERBATIM (``b2s_add_prepared``): a directory written by ``save`` holds the rows as
+        the index held them (already unit-normalised under ``metric="cosine"``), so any number of
+        save / load cycles is bit-stable and an ``inner_product`` index is never silently normalised.
+        The bf16 side-car is used only if it belongs to this ``index.faiss`` (same row count and
+        dimension, not older than it) and was written under the metric this object was constructed
+        with; a mismatching metric raises ``IndexBuildError``.
+        """
         d = Path(index_dir)
         if not d.exists():
             raise IndexNotFoundError(str(d))
@@ -274,10 +283,25 @@ class FlatIPIndex:
         L = _lib.lib()
         rows_src: Optional[np.ndarray] = None
         is_bf16 = False
-        if meta_p.exists() and side_p.exists():
+        use_side = meta_p.exists() and side_p.exists()
+        meta: Dict[str, Any] = {}
+        if use_side:
             meta = json.loads(meta_p.read_text())
+            if faiss_p.exists():
+                # a side-car left behind by an earlier save must not shadow a newer / different index.faiss
+                try:
+                    f_dim, f_n, _m = faiss_io.read_header(faiss_p)
+                except ValueError:
+                    f_dim, f_n = meta.get("dim"), meta.get("ntotal")   # not a flat file: the side-car decides
+                stale = faiss_p.stat().st_mtime > max(side_p.stat().st_mtime, meta_p.stat().st_mtime) + 2.0
+                if f_dim != meta.get("dim") or f_n != meta.get("ntotal") or stale:
+                    use_side = False
+        if use_side:
             if meta.get("dim") != self.embedding_dim:
                 raise IndexBuildError(f"index dim {meta.get('dim')} != embedding_dim {self.embedding_dim}")
+            saved_metric = meta.get("metric", self.metric)
+            if _METRIC_ALIASES.get(saved_metric, saved_metric) != _METRIC_ALIASES.get(self.metric, self.metric):
+                raise IndexBuildError(f"index was saved with metric {saved_metric!r}, this index uses {self.metric!r}")
             n = int(meta["ntotal"])
             if side_p.stat().st_size != n * self.embedding_dim * 2:
                 raise IndexBuildError(f"{side_p} has the wrong size for {n} rows")
@@ -286,11 +310,13 @@ class FlatIPIndex:
             is_bf16 = True
         elif faiss_p.exists():
             try:
-                rows_src, _metric = faiss_io.read_flat(faiss_p)
+                rows_src, f_metric = faiss_io.read_flat(faiss_p)
             except ValueError as e:
                 raise IndexBuildError(str(e)) from e
             if rows_src.shape[1] != self.embedding_dim:
                 raise IndexBuildError(f"index dim {rows_src.shape[1]} != embedding_dim {self.embedding_dim}")
+            if f_metric != 0:   # faiss METRIC_INNER_PRODUCT = 0: cosine and inner_product are both stored that way
+                raise IndexBuildError(f"index.faiss has metric_type {f_metric}; only inner-product (0) files are served")
         else:
             raise IndexNotFoundError(str(faiss_p))
         h = self._ensure()
@@ -298,10 +324,10 @@ class FlatIPIndex:
         n = rows_src.shape[0]
         if n:
             _check(L.b2s_reserve(h, n), "b2s_reserve")
+        dt = _lib.DTYPE_BF16 if is_bf16 else _lib.DTYPE_F32
         for s in range(0, n, block_rows):
             blk = np.ascontiguousarray(rows_src[s:s + block_rows])
-            fn = L.b2s_add_bf16 if is_bf16 else L.b2s_add_f32
-            _check(fn(h, blk.ctypes.data_as(ctypes.c_void_p), blk.shape[0], 0), "b2s_add")
+            _check(L.b2s_add_prepared(h, blk.ctypes.data_as(ctypes.c_void_p), dt, blk.shape[0], 0), "b2s_add_prepared")
         ids_p = d / "doc_ids.json"
         if ids_p.exists():
             with open(ids_p) as f:
@@ -349,8 +375,12 @@ class FlatIPIndex:
         return scores, ids
 
     def search_device(self, q: "torch.Tensor", k: int,
-                      out: Optional[Tuple["torch.Tensor", "torch.Tensor"]] = None):
-        """Device-resident search on torch's current stream (no host sync, no copies)."""
+                      out: Optional[Tuple["torch.Tensor", "torch.Tensor"]] = None, stable_queries: bool = False):
+        """Device-resident search on torch's current stream (no host sync, no copies).
+
+        ``stable_queries=True`` is the caller's promise that ``q`` was completely written before the
+        previous operation on this stream was enqueued (``B2S_SEARCH_STABLE_QUERIES``): a batch-1/2
+        scan may then overlap the tail of the previous search."""
         if self._h is None:
             raise IndexNotBuiltError()
         if q.device.index != self._device:
@@ -369,8 +399,36 @@ class FlatIPIndex:
             dt = _lib.DTYPE_BF16 if q.dtype == torch.bfloat16 else _lib.DTYPE_F32
             _check(_lib.lib().b2s_search_device(self._h, ctypes.c_void_p(q.data_ptr()), dt, nq, int(k),
                                                 ctypes.c_void_p(scores.data_ptr()), ctypes.c_void_p(ids.data_ptr()),
-                                                ctypes.c_void_p(stream)), "b2s_search_device")
+                                                ctypes.c_void_p(stream),
+                                                _lib.SEARCH_STABLE_QUERIES if stable_queries else 0), "b2s_search_device")
         return scores, ids
+
+    def read_trace(self, raw: bool = False) -> Optional[Dict[str, Any]]:
+        """Phase stamps of the last batch-1/2 scan launch (option ``trace`` = 1), in microseconds relative to
+        the earliest CTA start: see ``b2s_read_trace``.  Synchronises the device."""
+        if self._h is None:
+            raise IndexNotBuiltError()
+        stride = 512
+        buf = np.zeros(16 + 6 * stride, dtype=np.uint64)
+        n = _lib.lib().b2s_read_trace(self._h, buf.ctypes.data_as(ctypes.c_void_p), len(buf))
+        if n <= 0 or buf[1] == 0 or not (0 < int(buf[0]) <= stride):
+            return None
+        g = int(buf[0])
+        arr = lambda i: buf[16 + i * stride:16 + i * stride + g].astype(np.int64)   # noqa: E731
+        starts, ends = arr(0), arr(1)
+        t0 = int(starts.min())
+        us = lambda v: (int(v) - t0) / 1e3   # noqa: E731
+        out = {"grid": g, "cta_start_spread_us": us(starts.max()), "scan_end_first_us": us(ends.min()),
+               "scan_end_median_us": us(np.median(ends)), "scan_end_last_us": us(ends.max()), "ticket_us": us(buf[1]),
+               "local_topk_us": us(buf[2]), "done_us": us(buf[5])}
+        if buf[13]:
+            out["phase_b_offers"], out["phase_b_inserts"], out["transition_keys"] = int(buf[11]), int(buf[12]), int(buf[13])
+        if buf[3] and buf[4]:
+            out["pushed_us"], out["peers_seen_us"] = us(buf[3]), us(buf[4])
+        if raw:
+            out["raw"] = {"start": (starts - t0) / 1e3, "end": (ends - t0) / 1e3, "trans_begin": (arr(2) - t0) / 1e3,
+                          "trans_end": (arr(3) - t0) / 1e3, "static_end": (arr(4) - t0) / 1e3, "smid": arr(5)}
+        return out
 
     def stats(self) -> Dict[str, Any]:
         if self._h is None:

@@ -50,18 +50,6 @@ def retrieve_topk(index: FlatIPIndex, query_embs, k: int):
     return index.search(query_embs, k)[1]
 
 
-def maxsim_aggregation(chunk_scores) -> Dict[str, float]:
-    """Same contract as the reference's ``maxsim_aggregation`` (``src/utils/chunk.py:123-148``):
-    ``[(chunk_id "{doc_id}_{chunk_idx}", score), ...] -> {doc_id: max score}`` (host-side, for the
-    string-keyed lists the reference passes around; the device twin is ``maxsim_topk``)."""
-    doc_scores: Dict[str, float] = {}
-    for chunk_id, score in chunk_scores:
-        doc_id = "_".join(chunk_id.split("_")[:-1]) if "_" in chunk_id else chunk_id
-        if doc_id not in doc_scores or score > doc_scores[doc_id]:
-            doc_scores[doc_id] = score
-    return doc_scores
-
-
 def maxsim_topk(index: FlatIPIndex, query_embs, k: int, chunk_to_doc, k_chunks: Optional[int] = None):
     """Document-level top-k by MaxSim: search ``k_chunks`` (default 4k) chunk rows per query, keep each
     document's best chunk (``b2s_maxsim_device``).  ``chunk_to_doc``: int64 ``[ntotal]``, chunk row ->

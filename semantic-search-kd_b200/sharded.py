@@ -131,9 +131,7 @@ class ShardedFlatIPIndex:
             mine = gathered[self.rank]
             ids = mine[: nq * k * 8].view(torch.int64).view(nq, k)
             scores = mine[nq * k * 8: nq * k * 12].view(torch.float32).view(nq, k)
-            out_s = torch.empty((nq, k), dtype=torch.float32, device=device)
-            out_i = torch.empty((nq, k), dtype=torch.int64, device=device)
-            b = (gathered, mine, scores, ids, out_s, out_i)
+            b = (gathered, mine, scores, ids, None, None)
             self._bufs = {key: b}  # keep only the latest shape
         return b
 
@@ -167,11 +165,14 @@ class ShardedFlatIPIndex:
         return int(_lib.lib().b2s_exchange_status(self.local._h))
 
     def _peer_ok(self, nq: int, k: int) -> bool:
+        # (fp32 re-ranking happens after a LOCAL search only: with keep_fp32 the all-gather path is used)
         return (self.exchange == "peer" and self.world > 1 and nq <= self._ex_max_nq and
-                packed_bytes(nq, k) <= self._ex_slot_bytes and self.world * k <= 4096)
+                packed_bytes(nq, k) <= self._ex_slot_bytes and not getattr(self.local, "_keep_fp32", False))
 
-    def search_device(self, q: "torch.Tensor", k: int):
-        """Device-resident sharded search on the current stream; returns CUDA tensors (all ranks)."""
+    def search_device(self, q: "torch.Tensor", k: int, stable_queries: bool = False):
+        """Device-resident sharded search on the current stream; returns freshly allocated CUDA tensors
+        (all ranks hold the global answer).  ``stable_queries``: see ``FlatIPIndex.search_device``.
+        A peer-exchange timeout of an earlier call surfaces here as ``DeviceError``."""
         if self.n_total == 0 and self.local.ntotal == 0 and self.local._h is None:
             raise IndexNotBuiltError()
         nq = q.shape[0]
@@ -183,22 +184,20 @@ class ShardedFlatIPIndex:
             if q.dtype not in (torch.float32, torch.bfloat16):
                 q = q.float()
             q = q.contiguous()
-            key = ("peer", nq, k, str(q.device))
-            b = self._bufs.get(key)
-            if b is None:
-                b = (torch.empty((nq, k), dtype=torch.float32, device=q.device),
-                     torch.empty((nq, k), dtype=torch.int64, device=q.device))
-                self._bufs = {key: b}
-            out_s, out_i = b
+            out_s = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+            out_i = torch.empty((nq, k), dtype=torch.int64, device=q.device)
             stream = torch.cuda.current_stream(q.device).cuda_stream
             dt = _lib.DTYPE_BF16 if q.dtype == torch.bfloat16 else _lib.DTYPE_F32
             _check(_lib.lib().b2s_search_sharded_device(self.local._h, ctypes.c_void_p(q.data_ptr()), dt, nq, int(k),
                                                         ctypes.c_void_p(out_s.data_ptr()),
-                                                        ctypes.c_void_p(out_i.data_ptr()), ctypes.c_void_p(stream), 0),
+                                                        ctypes.c_void_p(out_i.data_ptr()), ctypes.c_void_p(stream), 0,
+                                                        _lib.SEARCH_STABLE_QUERIES if stable_queries else 0),
                    "b2s_search_sharded_device")
             return out_s, out_i
-        gathered, mine, scores, ids, out_s, out_i = self._buffers(nq, k, q.device)
-        self.local.search_device(q, k, out=(scores, ids))
+        gathered, mine, scores, ids, _os, _oi = self._buffers(nq, k, q.device)
+        out_s = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        self.local.search_device(q, k, out=(scores, ids), **({"stable_queries": True} if stable_queries else {}))
         if self.world > 1:
             dist.all_gather_into_tensor(gathered.view(-1), mine, group=self.group)
         if self._merge_fn is not None:

@@ -59,7 +59,7 @@ def test_emulated_ranks_two_phase(oracle, world, n, nq, k, path):
         for phase in (1, 2):
             for idx, (s, i) in zip(ranks, outs):
                 rc = L.b2s_search_sharded_device(idx._h, ctypes.c_void_p(q.data_ptr()), 0, nq, k,
-                                                 ctypes.c_void_p(s.data_ptr()), ctypes.c_void_p(i.data_ptr()), stream, phase)
+                                                 ctypes.c_void_p(s.data_ptr()), ctypes.c_void_p(i.data_ptr()), stream, phase, 0)
                 assert rc == 0, pkg._lib.last_error()
         torch.cuda.synchronize()
         for idx in ranks:
@@ -100,7 +100,7 @@ def test_exchange_rejects_oversized_calls():
     L = pkg._lib.lib()
     X = unit_rows(1000, 384, 1)
     (idx,) = _emulated_ranks(pkg, X, 1, 0)
-    rc = L.b2s_search_sharded_device(idx._h, ctypes.c_void_p(1), 0, 5000, 10, ctypes.c_void_p(1), ctypes.c_void_p(1), None, 0)
+    rc = L.b2s_search_sharded_device(idx._h, ctypes.c_void_p(1), 0, 5000, 10, ctypes.c_void_p(1), ctypes.c_void_p(1), None, 0, 0)
     assert rc == pkg._lib.B2S_ERR_UNSUPPORTED
     idx.close()
 
