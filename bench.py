@@ -37,7 +37,6 @@ K = 10
 METRIC = "queries/sec exact top-10 over 8.8Mx384"
 BLOCK = 1 << 20             # synthetic corpus is generated in 1 Mi-row blocks, seed = (seed, block)
 CPU_SAMPLE_DIV = 8          # the CPU legs scan 1/8 of the rows and scale the time by 8
-TIMING_EVERY = 8            # the library records its CUDA events on every 8th search of the timed region
 
 
 def peaks():
@@ -298,6 +297,8 @@ def run_ours(args):
     import torch.distributed as dist
     import semantic_search_kd_b200 as pkg
     from semantic_search_kd_b200.sharded import ShardedFlatIPIndex, shard_range
+    sys.path.insert(0, str(ROOT / "tools"))
+    import bench_extras as bx
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -313,9 +314,11 @@ def run_ours(args):
     # ---- build the (sharded) index --------------------------------------------------------
     lo, hi = shard_range(args.rows, world, rank)
     local = pkg.FlatIPIndex(DIM, metric="inner_product", device=local_rank)
-    local.set_option("timing", 1)
     if args.path:
         local.set_option("path", args.path)
+    for o in args.opt:
+        name, val = o.split("=")
+        local.set_option(name, int(val))
     local.reserve(hi - lo)
     t_build = time.perf_counter()
     for blk in make_rows(torch, lo, hi, dev):
@@ -323,22 +326,29 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
     if world > 1:
-        idx = ShardedFlatIPIndex(DIM, metric="inner_product", local_index=local, exchange=args.exchange)
+        idx = ShardedFlatIPIndex(DIM, metric="inner_product", local_index=local, exchange=args.exchange,
+                                 exchange_slot_bytes=16 << 20)
         idx.local.set_id_offset(lo)
         idx.n_total, idx.range = args.rows, (lo, hi)
     else:
         idx = local
 
-    # ---- queries: 1024 distinct, resident in HBM (value) and in pinned host memory (e2e) ----
+    # ---- queries: 1024 distinct, written once: resident in HBM (value) and in host memory (e2e) ----
     nqd = 1024
     g = torch.Generator(device=dev)
     g.manual_seed(1_000_003)
     Qd = torch.randn((nqd, DIM), generator=g, device=dev, dtype=torch.float32)
     Qd = (Qd / Qd.norm(dim=1, keepdim=True)).contiguous()
     Qh = Qd.cpu().numpy()
+    torch.cuda.synchronize()
 
-    def step_dev(i):
-        return idx.search_device(Qd[i % nqd:i % nqd + 1], K)
+    # The query set is complete before the first search is enqueued and is never written again: exactly the
+    # promise of B2S_SEARCH_STABLE_QUERIES (include/b200search.h), so the scan of query i+1 may overlap the
+    # candidate merge / NVLink exchange of query i.  `--no-stable` times the same loop without the promise.
+    stable = not args.no_stable
+
+    def step_dev(i, st=stable):
+        return idx.search_device(Qd[i % nqd:i % nqd + 1], K, stable_queries=st)
 
     def barrier():
         torch.cuda.synchronize()
@@ -346,17 +356,28 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def timed_loop(steps, st):
+        for i in range(max(3, min(args.warmup, 50))):
+            step_dev(i, st)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            step_dev(args.warmup + i, st)
+        b.record()
+        barrier()
+        return a.elapsed_time(b)
+
+    local.set_option("timing", 0)
     for i in range(args.warmup):
         step_dev(i)
     barrier()
-    # CUDA events around the dominant kernel on every 8th step: events between kernels switch programmatic
-    # dependent launch off for that call, sampling leaves the other 7 of 8 steps as a user would run them
-    local.set_option("timing", TIMING_EVERY)   # resets the ring
     clocks = Clocks(local_rank)
     if rank == 0:
         clocks.start()
         time.sleep(0.25)
     barrier()
+    # ---- the timed region: exactly K steps, one kernel launch each, CUDA events on the launching stream ----
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
@@ -369,30 +390,30 @@ def run_ours(args):
     launches_per_step = st["kernel_launches"] + (1 if exchange == "nccl" else 0)
     clk = clocks.stop() if rank == 0 else None
 
-    # dominant-kernel (K1) durations recorded by the library inside the timed region
-    nread = min((args.steps + TIMING_EVERY - 1) // TIMING_EVERY, 4096)
-    dom = np.zeros(nread, np.float32)
-    tot = np.zeros(nread, np.float32)
-    got = pkg._lib.lib().b2s_read_timings(local._h, dom.ctypes.data_as(ctypes.c_void_p),
-                                          tot.ctypes.data_as(ctypes.c_void_p), nread)
-    dom = dom[:got][dom[:got] > 0]
-    k1_ms = float(dom.mean()) if len(dom) else float("nan")
+    # ---- the same K steps without the stable-queries promise (informational) ----
+    other_ms = timed_loop(args.steps, not stable)
 
-    # ---- informational: back-to-back device calls with the scan of query i+1 overlapping the merge
-    # (and, multi-GPU, the exchange) of query i -- option "pdl"=2; the query buffer is static here
+    # ---- the dominant kernel alone: CUDA events recorded by the library around every launch of a separate loop
+    # (an event between two kernels switches their overlap off, so this is NOT done inside the timed region) ----
+    iso_n = max(8, min(64, args.steps))
+    local.set_option("timing", 1)   # resets the ring
+    for i in range(iso_n):
+        step_dev(i, False)
+    barrier()
+    dom = np.zeros(iso_n, np.float32)
+    tot = np.zeros(iso_n, np.float32)
+    got = pkg._lib.lib().b2s_read_timings(local._h, dom.ctypes.data_as(ctypes.c_void_p),
+                                          tot.ctypes.data_as(ctypes.c_void_p), iso_n)
+    dom = dom[:got][dom[:got] > 0]
+    tot = tot[:got][tot[:got] > 0]
+    k1_iso_ms = float(np.median(dom)) if len(dom) else float("nan")
     local.set_option("timing", 0)
-    local.set_option("pdl", 2)
-    for i in range(5):
-        step_dev(i)
-    barrier()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    for i in range(args.steps):
-        step_dev(args.warmup + i)
-    p1.record()
-    barrier()
-    pipe_ms = p0.elapsed_time(p1)
-    local.set_option("pdl", 1)
+
+    # ---- where a step's time goes: the kernel's own %globaltimer stamps ----
+    try:
+        breakdown = bx.tail_breakdown(torch, dist, idx, local, Qd, K, world, rank, n=16)
+    except Exception as e:  # never lose the main number
+        breakdown = {"error": str(e)}
 
     # ---- e2e: host buffers through the public search(), copies inside the timed region -------
     e2e_steps = max(10, min(args.steps, args.e2e_steps))
@@ -407,45 +428,73 @@ def run_ours(args):
         lat[i] = time.perf_counter() - t1
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    tot = tot[:got][tot[:got] > 0]
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([ms, e2e_s, k1_ms, pipe_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, k1_iso_ms, other_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s, k1_ms, pipe_ms = [float(x) for x in t.tolist()]
+        ms, e2e_s, k1_iso_ms, other_ms = [float(x) for x in t.tolist()]
 
-    # sanity: device path and host path agree on a query
+    # ---- parity (untimed): device path vs a torch fp32 reference over the same rows; host path == device path ----
+    try:
+        parity = bx.verify_parity(torch, dist, idx, make_rows, args.rows, DIM, world, rank, dev, lo, hi)
+    except Exception as e:
+        parity = {"ok": False, "error": repr(e)}
     sd, idd = idx.search_device(Qd[5:6], K)
     sh, ih = idx.search(Qh[5:6], K)
     agree = bool(np.array_equal(idd.cpu().numpy(), ih))
+    parity["host_api_equals_device_api"] = agree
+    parity["ok"] = bool(parity.get("ok")) and agree
 
     ex_status = idx.exchange_status() if world > 1 and hasattr(idx, "exchange_status") else 0
     exchange = getattr(idx, "exchange", None) if world > 1 else None   # may have fallen back to nccl
+    extras = {}
+    if (n_gpus == 8 or args.extras) and not args.no_extras:
+        # BASELINE configs[2] and configs[3], bounded (the driver's 8-GPU run makes them visible)
+        try:
+            extras["cfg_ance"] = bx.cfg_ance_report(torch, dist, pkg, idx, local, DIM, args.rows, world, rank, local_rank, dev,
+                                                    nq_total=args.ance_queries)
+        except Exception as e:
+            extras["cfg_ance"] = {"error": repr(e)}
+        try:
+            extras["cfg_100m"] = bx.cfg_100m_report(torch, dist, pkg, make_rows, DIM, world, rank, local_rank, dev,
+                                                    rows=args.rows_100m)
+        except Exception as e:
+            extras["cfg_100m"] = {"error": repr(e)}
     if rank == 0:
         peak, peak_src = peaks()
         local_bytes = (hi - lo) * DIM * 2   # rank 0's shard (ranges differ by at most one row)
-        achieved = local_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms == k1_ms else None
-        traffic = None
+        step_ms = ms / args.steps
+        k_launch_ms = step_ms / max(1, st["kernel_launches"])
+        achieved = local_bytes / (k_launch_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, None
         tp = ROOT / "profiles" / "traffic.json"
         if tp.exists() and n_gpus == 1:
             try:
-                traffic = json.loads(tp.read_text()).get("scan_topk_kernel_dram_bytes_per_launch")
+                tj = json.loads(tp.read_text())
+                traffic = tj.get("scan_topk_kernel_dram_bytes_per_launch")
+                traffic_src = "static file profiles/traffic.json (one `ncu --set full` capture: %s), not measured in this run" % tj.get("source")
             except Exception:
                 traffic = None
         value = args.steps / (ms * 1e-3)
         line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": n_gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(n_gpus),
-                "roofline": {"bound": "hbm", "kernel": "scan_topk_kernel (K1; its last CTA also merges the candidate lists"
-                                                       + (" and exchanges them with the peers)" if n_gpus > 1 else ")"), "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "config": dict(workload_config(n_gpus), stable_queries=stable,
+                               queries="device-resident set written before the first search and never rewritten: the loop "
+                                       "passes B2S_SEARCH_STABLE_QUERIES" if stable else "no promise about the query buffer"),
+                "roofline": {"bound": "hbm", "kernel": "scan_topk_kernel (K1; its last CTA also finishes the top-k"
+                                                       + (" and exchanges it with the peers over NVLink)" if n_gpus > 1 else ")"),
+                             "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": local_bytes,
-                             "kernel_ms_avg": k1_ms, "kernel_samples": int(len(dom)),
-                             "timing": f"CUDA events recorded by the library around the kernel on every {TIMING_EVERY}th step "
-                                       "of the timed region, on the stream the kernel runs on",
-                             "whole_step_frac": (local_bytes / (ms / args.steps * 1e-3) / 1e9) / peak},
+                             "kernel_ms_avg": k_launch_ms, "kernel_samples": args.steps,
+                             "timing": "steady state: the timed region's CUDA events (launching stream) bracket exactly "
+                                       f"{args.steps} back-to-back launches of this kernel, one per step; average = region / launches",
+                             "isolated_kernel_ms": k1_iso_ms, "isolated_samples": int(len(dom)),
+                             "isolated_frac": (local_bytes / (k1_iso_ms * 1e-3) / 1e9 / peak) if k1_iso_ms == k1_iso_ms else None,
+                             "isolated_timing": "median of CUDA events the library records around each launch of a separate "
+                                                "loop after the timed region (no overlap between consecutive launches)"},
                 "e2e": {"value": e2e_steps / e2e_s, "unit": "queries/s", "steps": e2e_steps,
                         "h2d_bytes_per_step": DIM * 4, "d2h_bytes_per_step": K * 12,
                         "api": "FlatIPIndex.search(np.ndarray, k) -> b2s_search (host buffers)" if world == 1
@@ -454,18 +503,25 @@ def run_ours(args):
                                "device_p50": float(np.percentile(tot, 50)) if len(tot) else None,
                                "device_p99": float(np.percentile(tot, 99)) if len(tot) else None,
                                "note": "e2e = wall time of one search(np.ndarray, k) call on rank 0; device = CUDA events "
-                                       "around one whole search call inside the timed region (rank 0)"},
-                "pipelined": {"value": args.steps / (pipe_ms * 1e-3), "unit": "queries/s", "ms_per_step": pipe_ms / args.steps,
-                              "note": "NOT the headline: same K steps with option pdl=2 (programmatic dependent launch lets "
-                                      "the scan of query i+1 overlap the merge/exchange of query i; needs a query buffer "
-                                      "that is not written by the immediately preceding kernel)"},
+                                       "around one whole search call (rank 0, separate loop)"},
+                ("without_stable_queries" if stable else "with_stable_queries"):
+                    {"value": args.steps / (other_ms * 1e-3), "unit": "queries/s", "ms_per_step": other_ms / args.steps,
+                     "note": "NOT the headline: the same K steps " + ("without" if stable else "with") +
+                             " the B2S_SEARCH_STABLE_QUERIES promise"},
+                "tail_breakdown_us": breakdown,
+                "parity": parity,
                 "gpu_launches": launches_per_step * args.steps,
                 "clocks": clk, "build_s": round(t_build, 2), "paths_agree": agree, "exchange_timeouts": ex_status}
+        line.update(extras)
         if n_gpus == 1 and not args.no_batched:
             try:
                 line["batched"] = batched_report(torch, local, dev)
             except Exception as e:
                 line["batched"] = {"error": str(e)}
+            try:
+                line["sweep"] = bx.sweep_report(torch, local, dev, DIM)
+            except Exception as e:
+                line["sweep"] = {"error": repr(e)}
         if n_gpus == 1 and not args.no_cpu:
             try:
                 qps, info = cpu_flat_qps(args.cpu_queries)
@@ -486,6 +542,8 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not parity.get("ok"):
+        raise SystemExit("bench.py: parity violated: " + json.dumps(parity)[:2000])
 
 
 def main():
@@ -501,6 +559,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-hnsw", action="store_true")
     ap.add_argument("--no-batched", action="store_true")
+    ap.add_argument("--no-stable", action="store_true", help="time the loop without B2S_SEARCH_STABLE_QUERIES")
+    ap.add_argument("--extras", action="store_true", help="run the bounded configs[2]/[3] legs at this N (default: N = 8 only)")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--rows-100m", type=int, default=100_000_000)
+    ap.add_argument("--ance-queries", type=int, default=32768)
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (repeatable)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="multi-GPU candidate exchange: fused peer-memory kernel (default) or NCCL all-gather")
     args = ap.parse_args()

@@ -130,6 +130,8 @@ B2S_API int b2s_set_id_offset(b2s_index* idx, int64_t offset);
  *                 | 2 treat every device call as if B2S_SEARCH_STABLE_QUERIES were set (per handle)
  *   "pdl_early"   1 (default): the scan kernel triggers its dependent launch at its start, so the next search's
  *                 CTAs take over SM slots as this one's retire (no launch gap); 0 = after the scan
+ *   "grid_spare"  CTA slots a fused-tail scan launch leaves free for its predecessor's last CTA (default 1)
+ *   "cascade_min_units" static iterations per warp below which the cascade select is not used (default 32)
  *   "prefetch_iters" scan kernel: iterations per warp prefetched into L2 before the PDL wait (default 6)
  *   "dynamic_tail"   scan kernel: units per CTA dealt by ticket at the end of the scan (default 3, 0 = static)
  *   "cascade"     1 (default): k <= 16 on large shards keeps the running global top-k in k sorted
@@ -293,7 +295,9 @@ B2S_API int b2s_read_timings(const b2s_index* idx, float* dominant_ms, float* to
  * ready, 3 = pushed to the peer ranks, 4 = every peer's candidates have arrived, 5 = outputs written,
  * word 0 = G (CTAs); then six arrays of 512 words, entry b = CTA b: start (after the dependency
  * wait), end of scan, cascade transition begin / end, end of the static part, SM id.
- * Synchronises the device and copies up to max_words words (16 + 6 * 512 for all); returns the count.
+ * Two such blocks are kept and used alternately (consecutive launches may overlap): the block of the LAST
+ * traced launch comes first, then that of the launch before it.
+ * Synchronises the device and copies up to max_words words (2 * (16 + 6 * 512) for all); returns the count.
  */
 B2S_API int b2s_read_trace(b2s_index* idx, uint64_t* out, int max_words);
 

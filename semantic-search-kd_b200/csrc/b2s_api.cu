@@ -150,17 +150,20 @@ struct b2s_index {
     int ex_fused = 0;
     // device control block of the scan kernel: done ticket, dynamic-tail work counters, the cascade select's
     // global slots [kScanMaxNQ][kCascadeMaxK] u64 -- all zero between launches
-    unsigned* done_counter = nullptr;
-    unsigned* work_counter = nullptr;
-    u64* gslots = nullptr;
+    ScanCtl* ctl = nullptr;             // two sets, used alternately by consecutive scan launches
+    unsigned ctl_launches = 0;          // counted scan launches so far: launch n uses set n & 1 and expects epoch n >> 1
+    bool ctl_prev_counted = false;      // the previous scan launch took part in the epoch protocol (not graph-captured)
     unsigned long long* trace_buf = nullptr;   // option "trace": globaltimer stamps of the last scan launch
     int opt_trace = 0;
+    unsigned trace_seq = 0;                    // the buffer has two halves used alternately (overlapping launches)
     int opt_prefetch_iters = 6;         // iterations per warp prefetched into L2 before the PDL wait (0 = off)
     int opt_dynamic_tail = 3;           // units per CTA dealt dynamically at the end of the scan (0 = all static)
     int opt_cascade = 1;                // k <= 16 on large shards: global sorted slots instead of per-CTA lists
     int opt_phase_a = 0;                // cascade: iterations against the local lists first (0 = auto)
     int opt_phase_a_stagger = 64;       // cascade: CTA b switches to the global slots b % this iterations later
-    int opt_transition_mode = 1;        // cascade: see ScanParams::transition_mode
+    int opt_transition_mode = 0;        // cascade: see ScanParams::transition_mode
+    int opt_grid_spare = 1;             // CTA slots left free by a fused-tail scan launch
+    int opt_cascade_min_units = 32;     // static iterations per warp below which the cascade select is not used
     int opt_pdl_early = 1;              // scan kernel triggers its dependent launch at its start (see ScanParams::early_trigger)
     int opt_peek_every = 0;             // cascade: iterations between re-reads of the slots' k-th key (0 = only after inserts)
     unsigned call_flags = 0;            // B2S_SEARCH_* of the call in flight
@@ -318,12 +321,22 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
     const int cap = list_capacity(k);
     const int rpi = scan_rows_per_iter(idx->dim);
     const int unit = rpi * kScanWarps;
+    const int max_group = scan_max_nq(idx->dim);
+    // One scan launch covers the whole call and nothing is seeded: the last CTA of the scan produces the
+    // final top-k (and, sharded with co-resident CTAs, the exchange) itself -- see scan_topk.cuh.
+    const bool fuse_tail = idx->opt_fused_tail && !seed && nq <= max_group && idx->ctl != nullptr &&
+                           (idx->ex_call == nullptr || idx->ex_fused);
     int grid = idx->num_sms * std::max(1, idx->opt_scan_ctas_per_sm);
+    // one CTA slot of the device stays free: the last CTA of a launch is still busy with the tail (read-out,
+    // NVLink exchange) when the next launch's CTAs move in, and none of those has to wait for its slot
+    if (fuse_tail && grid > idx->num_sms) grid -= std::max(0, std::min(idx->opt_grid_spare, idx->num_sms));
     const int64_t units = (idx->n + unit - 1) / unit;
     if ((int64_t)grid > units) grid = (int)units;
     grid = std::min(grid, kMergeMaxLists);
-    const int max_group = scan_max_nq(idx->dim);
     const bool pdl = idx->opt_pdl != 0;
+    cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cap_status) != cudaSuccess) cudaGetLastError();
+    const bool capturing = cap_status != cudaStreamCaptureStatusNone;
 
     const int chunk = (int)std::min<int64_t>(nq, kScanQueryChunk);
     int rc;
@@ -331,18 +344,14 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
     if ((rc = idx->ws_counts.ensure((size_t)grid * chunk * sizeof(int))) != B2S_OK) return rc;
     if (seed && (rc = idx->ws_seed.ensure((size_t)chunk * sizeof(u64))) != B2S_OK) return rc;
 
-    // One scan launch covers the whole call and nothing is seeded: the last CTA of the scan produces the
-    // final top-k (and, sharded with co-resident CTAs, the exchange) itself -- see scan_topk.cuh.
-    const bool fuse_tail = idx->opt_fused_tail && !seed && nq <= max_group && idx->done_counter != nullptr &&
-                           (idx->ex_call == nullptr || idx->ex_fused);
     // Dynamic tail: the first S units of every CTA are static, the rest of the shard is dealt by ticket.
     const int64_t full_units = idx->n / unit;
     const int64_t static_units = std::max<int64_t>(0, full_units / grid - idx->opt_dynamic_tail);   // S
-    const bool dyn_ok = idx->opt_dynamic_tail > 0 && idx->work_counter != nullptr && idx->done_counter != nullptr;
+    const bool dyn_ok = idx->opt_dynamic_tail > 0 && idx->ctl != nullptr;
     const long long dyn_begin = dyn_ok ? (long long)(static_units * grid * unit) : (long long)idx->n;
     // Cascade select: small k, one fused launch, enough static iterations for a meaningful phase A.
-    const bool cascade = idx->opt_cascade && fuse_tail && dyn_ok && idx->gslots != nullptr && k <= kCascadeMaxK &&
-                         static_units >= 8;
+    const bool cascade = idx->opt_cascade && fuse_tail && dyn_ok && k <= kCascadeMaxK &&
+                         static_units >= idx->opt_cascade_min_units;
     for (int64_t c0 = 0; c0 < nq; c0 += chunk) {
         const int cn = (int)std::min<int64_t>(chunk, nq - c0);
         for (int pass = seed ? 0 : 1; pass < 2; ++pass) {
@@ -366,12 +375,22 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
                 // The scan only READS the corpus and the caller's queries unless a kernel of THIS call
                 // ran before it (query prep, seeding pass, an earlier group writing the same workspace).
                 p.pdl_late_wait = (late_wait_ok && !seed && nq <= max_group) ? 1 : 0;
-                p.done_counter = idx->done_counter;
-                p.work_counter = idx->work_counter;
                 p.dyn_begin = pass == 1 ? dyn_begin : (long long)idx->n;   // the sampling pre-pass is all static
+                // control set: launches that use one (fused tail or dynamic tail) alternate between the two sets
+                const bool uses_ctl = idx->ctl != nullptr && (fuse_tail || p.dyn_begin < (long long)idx->n);
+                if (idx->ctl != nullptr) {
+                    p.ctl = idx->ctl + (idx->ctl_launches & 1u);
+                    p.ctl_expect = idx->ctl_launches >> 1;
+                    p.ctl_bump = (uses_ctl && !capturing) ? 1 : 0;
+                }
+                // overlap with the predecessor only inside an unbroken chain of counted launches
+                if (!idx->ctl_prev_counted || capturing || !uses_ctl) p.pdl_late_wait = 0;
                 p.prefetch_iters = pass == 1 ? std::min(32, std::max(0, idx->opt_prefetch_iters)) : 0;
-                p.trace = (idx->opt_trace && pass == 1) ? idx->trace_buf : nullptr;
-                p.early_trigger = idx->opt_pdl_early;
+                p.trace = (idx->opt_trace && pass == 1)
+                              ? idx->trace_buf + (size_t)(idx->trace_seq++ & 1u) * (kTraceWords + kTraceArrays * kTraceStride)
+                              : nullptr;
+                // early trigger unless this launch would park its CTAs on a full-grid wait in the middle of the scan
+                p.early_trigger = (idx->opt_pdl_early && (!p.pdl_late_wait || cascade)) ? 1 : 0;
                 if (inline_q != nullptr) {
                     p.use_inline = 1;
                     memcpy(p.q_inline, inline_q, (size_t)nq * idx->dim * sizeof(float));
@@ -391,7 +410,6 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
                     if (idx->ex_call) p.ex = *idx->ex_call;
                     if (cascade) {
                         p.select_mode = 1;
-                        p.gslots = idx->gslots;
                         p.peek_every = idx->opt_peek_every;
                         p.transition_mode = idx->opt_transition_mode;
                         // phase A ends (and, with stable queries, the PDL wait sits) after a0 + blockIdx % stagger
@@ -403,6 +421,8 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
                     }
                 }
                 if ((rc = launch_scan(idx->dim, group, p, grid, s, pdl)) != B2S_OK) return rc;
+                if (p.ctl_bump) ++idx->ctl_launches;
+                idx->ctl_prev_counted = p.ctl_bump != 0;
                 idx->stats.kernel_launches++;
                 if (pass == 1) idx->stats.passes++;
                 g0 += group;
@@ -705,16 +725,11 @@ B2S_API int b2s_create(int dim, int metric, int device, b2s_index** out) {
         delete idx;
         return fail(B2S_ERR_CUDA, "cudaStreamCreate failed");
     }
-    // [done ticket | kScanWarps work counters, one 128-byte line each | global slots of the cascade select]
-    constexpr size_t kSlotsOff = 128 * (1 + kScanWarps);
-    constexpr size_t kCtlBytes = kSlotsOff + (size_t)kScanMaxNQ * kCascadeMaxK * sizeof(u64);
-    if (cudaMalloc((void**)&idx->done_counter, kCtlBytes) != cudaSuccess ||
-        cudaMemset(idx->done_counter, 0, kCtlBytes) != cudaSuccess) {
+    // two control sets of the scan kernel (done ticket, dynamic-tail counters, cascade slots, epoch): all zero
+    if (cudaMalloc((void**)&idx->ctl, 2 * sizeof(ScanCtl)) != cudaSuccess ||
+        cudaMemset(idx->ctl, 0, 2 * sizeof(ScanCtl)) != cudaSuccess) {
         cudaGetLastError();
-        idx->done_counter = nullptr;   // the fused tail, the dynamic tail and the cascade select are simply not used
-    } else {
-        idx->work_counter = idx->done_counter + kWorkCounterStride;
-        idx->gslots = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(idx->done_counter) + kSlotsOff);
+        idx->ctl = nullptr;   // the fused tail, the dynamic tail and the cascade select are simply not used
     }
     *out = idx;
     return B2S_OK;
@@ -744,7 +759,7 @@ B2S_API int b2s_destroy(b2s_index* idx) {
     tensor_path_release(idx);
 #endif
     exchange_release(idx);
-    if (idx->done_counter) cudaFree(idx->done_counter);
+    if (idx->ctl) cudaFree(idx->ctl);
     if (idx->trace_buf) cudaFree(idx->trace_buf);
     if (idx->xs_event) cudaEventDestroy(idx->xs_event);
     if (idx->pin_q) cudaFreeHost(idx->pin_q);
@@ -926,13 +941,19 @@ B2S_API int b2s_set_option(b2s_index* idx, const char* name, int64_t value) {
     } else if (s == "phase_a_stagger") {
         if (value < 1 || value > 4096) return fail(B2S_ERR_INVALID, "phase_a_stagger must be in [1, 4096]");
         idx->opt_phase_a_stagger = (int)value;
+    } else if (s == "grid_spare") {
+        if (value < 0 || value > 64) return fail(B2S_ERR_INVALID, "grid_spare must be in [0, 64]");
+        idx->opt_grid_spare = (int)value;
+    } else if (s == "cascade_min_units") {
+        if (value < 4 || value > 1 << 20) return fail(B2S_ERR_INVALID, "cascade_min_units must be in [4, 2^20]");
+        idx->opt_cascade_min_units = (int)value;
     } else if (s == "pdl_early") {
         idx->opt_pdl_early = value ? 1 : 0;
     } else if (s == "trace") {
         if (value && !idx->trace_buf) {
             int rc = use_device(idx);
             if (rc != B2S_OK) return rc;
-            const size_t bytes = (size_t)(kTraceWords + kTraceArrays * kTraceStride) * sizeof(unsigned long long);
+            const size_t bytes = (size_t)2 * (kTraceWords + kTraceArrays * kTraceStride) * sizeof(unsigned long long);
             CUDA_TRY(cudaMalloc((void**)&idx->trace_buf, bytes));
             CUDA_TRY(cudaMemset(idx->trace_buf, 0, bytes));
         }
@@ -972,6 +993,8 @@ B2S_API int64_t b2s_get_option(const b2s_index* idx, const char* name) {
     if (s == "phase_a_stagger") return idx->opt_phase_a_stagger;
     if (s == "trace") return idx->opt_trace;
     if (s == "pdl_early") return idx->opt_pdl_early;
+    if (s == "grid_spare") return idx->opt_grid_spare;
+    if (s == "cascade_min_units") return idx->opt_cascade_min_units;
     if (s == "transition_mode") return idx->opt_transition_mode;
     if (s == "peek_every") return idx->opt_peek_every;
     if (s == "exchange_timeout_ms") return idx->ex.timeout_ms;
@@ -1199,9 +1222,16 @@ B2S_API int b2s_read_trace(b2s_index* idx, uint64_t* out, int max_words) {
     std::lock_guard<std::mutex> g(idx->mu);
     int rc = use_device(idx);
     if (rc != B2S_OK) return rc;
-    const int n = std::min(max_words, kTraceWords + kTraceArrays * kTraceStride);
+    constexpr int kHalf = kTraceWords + kTraceArrays * kTraceStride;
+    const int n = std::min(max_words, 2 * kHalf);
     CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpy(out, idx->trace_buf, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    // the half of the LAST traced launch first, then the launch before it
+    const unsigned last = (idx->trace_seq + 1u) & 1u;
+    const int n0 = std::min(n, kHalf);
+    CUDA_TRY(cudaMemcpy(out, idx->trace_buf + (size_t)last * kHalf, (size_t)n0 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (n > kHalf)
+        CUDA_TRY(cudaMemcpy(out + kHalf, idx->trace_buf + (size_t)(last ^ 1u) * kHalf, (size_t)(n - kHalf) * sizeof(uint64_t),
+                            cudaMemcpyDeviceToHost));
     return n;
 }
 

@@ -29,6 +29,15 @@
 //      slots' k-th key IS every CTA's threshold: a row that beats it is inserted straight away
 //      (~k ln(1/phase A fraction) insertions per query over the whole GPU).  When the scan ends the
 //      answer already sits sorted in the slots: the last CTA only reads k keys -- no merge.
+//      The switch from phase A to the slots is made warp by warp without a CTA barrier: the last warp
+//      of a CTA to get there flushes the CTA's list into the slots while the other seven stream on.
+//
+// Consecutive launches: the state launches share (done ticket, dynamic-tail counters, cascade slots)
+// exists TWICE (ScanCtl[2]) and is used alternately; the last CTA of a launch resets its set and
+// publishes that in the set's epoch word.  With B2S_SEARCH_STABLE_QUERIES and the cascade select a
+// launch therefore depends on its predecessor in ONE place only: its last CTA waits for the
+// predecessor grid before it writes outputs / talks to the peer ranks.  Everything else -- the whole
+// scan -- overlaps the predecessor's ragged end, top-k read-out and NVLink exchange.
 #pragma once
 #include "exchange.cuh"
 #include "merge_topk.cuh"
@@ -45,6 +54,15 @@ constexpr int kWorkCounterStride = 32;   // words between the dynamic tail's tic
 constexpr int kTraceWords = 16;          // header of the trace buffer, then kTraceArrays arrays of kTraceStride per-CTA stamps:
 constexpr int kTraceStride = 512;        //   0 start, 1 scan end, 2 transition begin, 3 transition end, 4 static part end, 5 SM id
 constexpr int kTraceArrays = 6;
+
+// State shared by consecutive launches; two sets, launch n of a handle uses set n & 1.
+struct ScanCtl {
+    unsigned done;                                      // CTAs that have finished (ticket); the last one resets the set
+    unsigned epoch;                                     // launches that have used AND reset this set (release store)
+    unsigned pad[30];
+    unsigned work[kScanWarps * kWorkCounterStride];     // dynamic-tail ticket counters, one 128-byte line each
+    u64 gslots[kScanMaxNQ * kCascadeMaxK];              // cascade select: running global top-k, sorted descending
+};
 
 struct ScanParams {
     const uint4* corpus;   // bf16 rows, row-major, dim*2 bytes each (16-byte aligned)
@@ -68,21 +86,23 @@ struct ScanParams {
     // separate merge kernel, no kernel boundary.  1 = write the final top-k (mp.out_*); 2 = sharded
     // search: push to the peers, wait, merge (ex).
     int fused_tail;
-    unsigned* done_counter;   // zero before the launch; the last CTA resets it
+    ScanCtl* ctl;             // this launch's control set (zero when its epoch reads ctl_expect)
+    unsigned ctl_expect;      // epoch value that says the set's previous user has reset it
+    int ctl_bump;             // 1: publish expect + 1 when the set has been reset.  0 (launch captured into a CUDA graph,
+                              // replayed any number of times): the launch is ordered by full grid dependencies on both
+                              // sides, resets the set and leaves the epoch alone
     MergeParams mp;
     ExchangeArgs ex;
     // dynamic tail: rows [dyn_begin, n_rows) are handed out 2U rows per ticket (dyn_begin == n_rows: all static)
-    long long dyn_begin;
-    unsigned* work_counter;   // kScanWarps counters, kWorkCounterStride words apart (one per region of the dynamic
-                              // tail: 2400 warps on one address would be bound by L2 atomic throughput); zero before
-                              // the launch, the last CTA resets them
+    long long dyn_begin;      // (ctl->work: kScanWarps counters, one per region of the dynamic tail -- 2400 warps on
+                              // one address would be bound by L2 atomic throughput)
     // cascade select
     int select_mode;          // 0 lists, 1 cascade
     int phase_a_iters;        // iterations every warp runs against the shared-memory lists first ...
     int phase_a_stagger;      // ... plus blockIdx % phase_a_stagger: the CTAs reach the slots a few at a time, so
                               // that the peek of a late CTA already sees (and is filtered by) the early ones' keys
-    u64* gslots;              // [kScanMaxNQ][kCascadeMaxK] running global top-k, zero before the launch
-    int transition_mode;      // 1 (default): the CTA waits for the bound, not for the insertion chain; 0 / 2: A/B variants
+    int transition_mode;      // 0 (default): CTA-wide switch behind a barrier; 1: warp-by-warp switch without a barrier
+                              // (A/B variant: no better in steady state, and more offers to the slots)
     int peek_every;           // phase B: warp 0 re-reads the slots' k-th key every this many iterations (0 = never)
     // L2 prefetch of this warp's first iterations, issued BEFORE the PDL wait: the corpus is immutable
     // while searches are in flight, so the idle DRAM time of the predecessor's tail is put to use
@@ -188,6 +208,8 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
     __shared__ float s_thr[NQ];
     __shared__ int s_count[NQ];
     __shared__ int s_lock[NQ];
+    __shared__ int s_arrived;                    // cascade: warps of this CTA that have left phase A
+    __shared__ u64 s_casc[NQ][kCascadeMaxK];     // cascade: the last CTA's copy of the slots
     auto list_of = [&](int q) { return ListRef{&s_thr_key[q], &s_thr[q], &s_count[q], &s_lock[q]}; };
 
     const int tid = threadIdx.x;
@@ -225,6 +247,7 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         p.trace[kTraceWords + 5 * kTraceStride + blockIdx.x] = smid;
     }
+    if (tid == 0) s_arrived = 0;
     if (tid < NQ) {
         u64 seed = 0ull;
         if (p.seed_keys != nullptr && tid < p.nq_valid) seed = p.seed_keys[p.q_begin + tid];
@@ -284,7 +307,7 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
             for (int i = 1; i < U; ++i) s = (hl == i) ? acc[q][i] : s;
             const bool pass = row_ok && (s >= *(volatile float*)&s_thr[q]);
             if (__any_sync(kFull, pass)) {
-                u64* slots = p.gslots + q * kCascadeMaxK;
+                u64* slots = p.ctl->gslots + q * kCascadeMaxK;
                 const u64 key = make_key(s, (uint32_t)myrow);
                 const bool ins = pass && key > *(volatile u64*)&s_thr_key[q];
                 cascade_insert_warp(slots, p.k, ins, key);
@@ -374,7 +397,7 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
         if (warp == 0 && p.peek_every > 0 && --peek_in == 0) {   // uniform
             peek_in = p.peek_every;
             peeked_q = peek_q;
-            g = ldcg_pinned_u64(p.gslots + peek_q * kCascadeMaxK + p.k - 1);
+            g = ldcg_pinned_u64(p.ctl->gslots + peek_q * kCascadeMaxK + p.k - 1);
             peek_q = peek_q + 1 < p.nq_valid ? peek_q + 1 : 0;
         }
         return g;
@@ -387,6 +410,16 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
     const uint4* rp = p.corpus + (base + half) * kChunksPerRow + hl;
     const long long rp_step = step * kChunksPerRow;
 
+    // The control set is ours once its epoch says that the launch before the previous one has reset it (with
+    // the early PDL wait the predecessor grid has completed and this passes at once).  Warp-collective.
+    auto ctl_ready = [&]() {
+        if (lane == 0) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu_u32(&p.ctl->epoch) != p.ctl_expect && clock64() - t0 < 4000000000ll) __nanosleep(64);
+        }
+        __syncwarp();
+    };
+
     // ---- static part, against the shared-memory lists (cascade: only the first phase_a_iters) ------
     {
         int it = 0;
@@ -396,34 +429,61 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
     }
     u64 g_bound = 0ull;   // cascade: the slots' k-th key as peeked one iteration ago (warp 0, lane = query)
     if (cascade) {
-        // ---- phase A -> B: warp q sorts query q's local list and adopts the better of its k-th key and the
-        // global slots' k-th key as the CTA's bound (one L2 round trip); after the second barrier the other
-        // warps go on against that bound while warp q alone walks the chain of atomics that offers the local
-        // top-k to the slots -- the CTA stalls for a load, not for the chain.
-        __syncthreads();                        // nobody appends to the shared-memory lists any more
-        stamp(2);
-        if (p.pdl_late_wait) grid_dep_wait();   // the predecessor has reset the slots / counters and is gone
-        int c_mine = 0;
-        if (warp < p.nq_valid) {                // warp-uniform
-            c_mine = list_compact_warp(list_of(warp), entries + (size_t)warp * p.cap, p.cap, p.k, lane);
-            if (p.transition_mode == 0)         // (A/B switch: the whole CTA waits for the chain)
-                cascade_insert_warp(p.gslots + warp * kCascadeMaxK, p.k, lane < c_mine,
-                                    entries[(size_t)warp * p.cap + (lane < c_mine ? lane : 0)]);
-            __syncwarp();
-            adopt_bound(warp, __ldcg(p.gslots + warp * kCascadeMaxK + p.k - 1));   // every lane: same word, same stores
+        // ---- phase A -> B, warp by warp, no CTA barrier: a warp that has done its phase A iterations goes on
+        // against the global slots at once (its bound: the CTA's list threshold, raised to the slots' k-th key
+        // whenever it looks).  The LAST warp of the CTA to arrive knows that nobody appends to the shared-memory
+        // lists any more: it alone sorts them and walks the chains of atomics that offer the CTA's local top-k to
+        // the slots, while the other seven warps keep streaming.
+        if (p.transition_mode == 0) {
+            // CTA-wide switch: barrier, warp q sorts query q's list and adopts the better of its k-th
+            // key and the slots' k-th key, barrier, the other warps go on while warp q walks the insertion chain
+            __syncthreads();
+            stamp(2);
+            if (p.pdl_late_wait) ctl_ready();
+            int c_mine = 0;
+            if (warp < p.nq_valid) {
+                c_mine = list_compact_warp(list_of(warp), entries + (size_t)warp * p.cap, p.cap, p.k, lane);
+                __syncwarp();
+                adopt_bound(warp, __ldcg(p.ctl->gslots + warp * kCascadeMaxK + p.k - 1));
+                __syncwarp();
+            }
+            __syncthreads();
+            if (warp < p.nq_valid) {
+                u64* slots = p.ctl->gslots + warp * kCascadeMaxK;
+                cascade_insert_warp(slots, p.k, lane < c_mine, entries[(size_t)warp * p.cap + (lane < c_mine ? lane : 0)]);
+                if (p.trace != nullptr && lane == 0) atomicAdd(p.trace + 10, (unsigned long long)c_mine);
+                __syncwarp();
+                adopt_bound(warp, __ldcg(slots + p.k - 1));
+                __syncwarp();
+                if (warp == 0) stamp(3);
+            }
+        } else {
+        if (warp == 0) stamp(2);
+        if (p.pdl_late_wait) ctl_ready();
+        __threadfence_block();
+        int arrived = 0;
+        if (lane == 0) arrived = atomicAdd(&s_arrived, 1);
+        arrived = __shfl_sync(kFull, arrived, 0);
+        if (arrived == kScanWarps - 1) {        // warp-uniform
+            __threadfence_block();
+            for (int q = 0; q < p.nq_valid; ++q) {
+                u64* slots = p.ctl->gslots + q * kCascadeMaxK;
+                u64* mine = entries + (size_t)q * p.cap;
+                const int c_mine = list_compact_warp(list_of(q), mine, p.cap, p.k, lane);
+                adopt_bound(q, __ldcg(slots + p.k - 1));
+                __syncwarp();
+                const u64 key = mine[lane < c_mine ? lane : 0];
+                cascade_insert_warp(slots, p.k, lane < c_mine && key > *(volatile u64*)&s_thr_key[q], key);
+                if (p.trace != nullptr && lane == 0) atomicAdd(p.trace + 10, (unsigned long long)c_mine);
+                __syncwarp();
+                adopt_bound(q, __ldcg(slots + p.k - 1));
+                __syncwarp();
+            }
+            if (p.trace != nullptr && lane == 0) p.trace[kTraceWords + 3 * kTraceStride + blockIdx.x] = globaltimer_ns();
+        } else {
+            for (int q = 0; q < p.nq_valid; ++q) adopt_bound(q, __ldcg(p.ctl->gslots + q * kCascadeMaxK + p.k - 1));
             __syncwarp();
         }
-        if (p.transition_mode != 2) __syncthreads();
-        if (warp < p.nq_valid) {
-            const int q = warp;
-            u64* slots = p.gslots + q * kCascadeMaxK;
-            if (p.transition_mode != 0)
-                cascade_insert_warp(slots, p.k, lane < c_mine, entries[(size_t)q * p.cap + (lane < c_mine ? lane : 0)]);
-            if (p.trace != nullptr && lane == 0) atomicAdd(p.trace + 10, (unsigned long long)c_mine);
-            __syncwarp();
-            adopt_bound(q, __ldcg(slots + p.k - 1));
-            __syncwarp();
-            if (warp == 0) stamp(3);
         }
         for (; base + kRowsPerIter <= static_end; base += step, rp += rp_step) {
             const u64 g = bound_peek();     // lands during this iteration's loads, applied at the start of the next
@@ -434,7 +494,9 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
     } else {
         // static tail (only when nothing is dealt dynamically): this warp's partial group, if any
         if (!dynamic && base < row_end) scan_rows_clamped(base, offer_list);
-        if (p.pdl_late_wait && dynamic) grid_dep_wait();   // the predecessor has reset the work counter
+        // lists mode: the candidate lists / counts workspace is read by the predecessor's merge until it completes
+        if (p.pdl_late_wait && dynamic) grid_dep_wait();
+        if (p.pdl_late_wait && dynamic) ctl_ready();
     }
 
     if (p.trace != nullptr && warp == 0 && lane == 0) p.trace[kTraceWords + 4 * kTraceStride + blockIdx.x] = globaltimer_ns();
@@ -449,7 +511,7 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
             const unsigned c0 = region * per_region;
             if (c0 >= n_chunks) continue;
             const unsigned cn = min(per_region, n_chunks - c0);
-            unsigned* ctr = p.work_counter + region * kWorkCounterStride;
+            unsigned* ctr = p.ctl->work + region * kWorkCounterStride;
             unsigned nxt = 0u;
             if (lane == 0) nxt = atomicAdd(ctr, 1u);
             nxt = __shfl_sync(kFull, nxt, 0);
@@ -474,7 +536,7 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
     }
     __syncthreads();
     stamp(1);
-    if (!p.early_trigger) grid_dep_launch();   // (A/B) the next kernel may be scheduled from here on
+    if (!p.early_trigger) grid_dep_launch();   // the next kernel may be scheduled from here on
 
     if (!cascade) {
         if (p.pdl_late_wait && !dynamic) grid_dep_wait();   // the previous call's merge has finished reading the lists
@@ -492,23 +554,22 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
     }
     if (p.fused_tail == 0 && !dynamic) return;
 
-    // ---- last CTA done (threadfence reduction pattern): resets the counters, runs the fused tail -----
+    // ---- last CTA done (threadfence reduction pattern): resets the control set, runs the fused tail -----
     __shared__ MergeSmem sm;
     __shared__ int s_last;
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        const unsigned ticket = atomicAdd(p.done_counter, 1u);
+        if (p.pdl_late_wait && !cascade && !dynamic) {   // (a set nobody has touched yet in this launch)
+            const long long t0 = clock64();
+            while (ld_acquire_gpu_u32(&p.ctl->epoch) != p.ctl_expect && clock64() - t0 < 4000000000ll) __nanosleep(64);
+        }
+        const unsigned ticket = atomicAdd(&p.ctl->done, 1u);
         s_last = ticket == gridDim.x - 1 ? 1 : 0;
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (tid == 0) {
-        *p.done_counter = 0u;   // ready for the next launch (stream-ordered after this kernel)
-    }
-    if (dynamic && tid < kScanWarps) p.work_counter[tid * kWorkCounterStride] = 0u;
-    if (p.fused_tail == 0) return;
     unsigned long long* tr = (p.trace != nullptr && tid == 0) ? p.trace : nullptr;
     if (tr) {
         tr[0] = gridDim.x;
@@ -516,19 +577,35 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
         tr[11] = tr[8], tr[12] = tr[9], tr[13] = tr[10];   // this launch's diagnostics counters
         tr[8] = tr[9] = tr[10] = 0ull;
     }
+    // Take what the set holds (cascade: the answer), reset it and hand it on: from the epoch store on, the
+    // launch after the next one may use the set -- before this CTA has written a single output.
+    if (cascade) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            u64* slots = p.ctl->gslots + q * kCascadeMaxK;
+            if (q < p.nq_valid && tid < kCascadeMaxK) {
+                s_casc[q][tid] = tid < p.k ? __ldcg(slots + tid) : 0ull;
+                slots[tid] = 0ull;
+            }
+        }
+    }
+    if (tid == 0) p.ctl->done = 0u;
+    if (dynamic && tid < kScanWarps) p.ctl->work[tid * kWorkCounterStride] = 0u;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0 && p.ctl_bump) st_release_gpu_u32(&p.ctl->epoch, p.ctl_expect + 1u);
+    if (p.fused_tail == 0) return;
+    // The one dependency on the predecessor launch under B2S_SEARCH_STABLE_QUERIES: outputs are written and the
+    // peer ranks are talked to in call order.
+    if (p.pdl_late_wait) grid_dep_wait();
     for (int q = 0; q < p.nq_valid; ++q) {
         const int lq = p.q_begin + q;     // list / output index of this query inside the call
         int kk;
         if (cascade) {
-            u64* slots = p.gslots + q * kCascadeMaxK;
-            if (tid < kCascadeMaxK) {
-                const u64 key = tid < p.k ? __ldcg(slots + tid) : 0ull;
-                sm.buf[tid] = key;
-                slots[tid] = 0ull;            // ready for the next launch
-            }
+            if (tid < kCascadeMaxK) sm.buf[tid] = s_casc[q][tid];
             __syncthreads();
             kk = 0;
-            for (int i = 0; i < p.k; ++i) kk += sm.buf[i] != 0ull;   // sorted: the non-empty slots are a prefix
+            for (int i = 0; i < p.k; ++i) kk += s_casc[q][i] != 0ull;   // sorted: the non-empty slots are a prefix
         } else {
             const int m_sorted = merge_lists_sorted<kScanThreads>(p.mp, lq, sm);
             kk = m_sorted < p.mp.k ? m_sorted : p.mp.k;

@@ -75,6 +75,15 @@ __device__ __forceinline__ void st_u64_if(u64* ptr, u64 v, bool pred) {
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // nanoseconds of the GPU-wide timer (comparable across SMs; ~32 ns granularity): option "trace" stamps
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;

@@ -403,31 +403,50 @@ class FlatIPIndex:
                                                 _lib.SEARCH_STABLE_QUERIES if stable_queries else 0), "b2s_search_device")
         return scores, ids
 
-    def read_trace(self, raw: bool = False) -> Optional[Dict[str, Any]]:
+    def read_trace(self, raw: bool = False, previous: bool = False) -> Optional[Dict[str, Any]]:
         """Phase stamps of the last batch-1/2 scan launch (option ``trace`` = 1), in microseconds relative to
-        the earliest CTA start: see ``b2s_read_trace``.  Synchronises the device."""
+        the earliest CTA start: see ``b2s_read_trace``.  ``previous=True`` adds the launch before it under
+        ``"previous"`` and ``"period_us"`` = distance between the two launches' earliest CTA starts (they may
+        overlap under programmatic dependent launch).  Synchronises the device."""
         if self._h is None:
             raise IndexNotBuiltError()
-        stride = 512
-        buf = np.zeros(16 + 6 * stride, dtype=np.uint64)
+        stride, half = 512, 16 + 6 * 512
+        buf = np.zeros(2 * half, dtype=np.uint64)
         n = _lib.lib().b2s_read_trace(self._h, buf.ctypes.data_as(ctypes.c_void_p), len(buf))
-        if n <= 0 or buf[1] == 0 or not (0 < int(buf[0]) <= stride):
+        if n <= 0:
             return None
-        g = int(buf[0])
-        arr = lambda i: buf[16 + i * stride:16 + i * stride + g].astype(np.int64)   # noqa: E731
-        starts, ends = arr(0), arr(1)
-        t0 = int(starts.min())
-        us = lambda v: (int(v) - t0) / 1e3   # noqa: E731
-        out = {"grid": g, "cta_start_spread_us": us(starts.max()), "scan_end_first_us": us(ends.min()),
-               "scan_end_median_us": us(np.median(ends)), "scan_end_last_us": us(ends.max()), "ticket_us": us(buf[1]),
-               "local_topk_us": us(buf[2]), "done_us": us(buf[5])}
-        if buf[13]:
-            out["phase_b_offers"], out["phase_b_inserts"], out["transition_keys"] = int(buf[11]), int(buf[12]), int(buf[13])
-        if buf[3] and buf[4]:
-            out["pushed_us"], out["peers_seen_us"] = us(buf[3]), us(buf[4])
-        if raw:
-            out["raw"] = {"start": (starts - t0) / 1e3, "end": (ends - t0) / 1e3, "trans_begin": (arr(2) - t0) / 1e3,
-                          "trans_end": (arr(3) - t0) / 1e3, "static_end": (arr(4) - t0) / 1e3, "smid": arr(5)}
+
+        def parse(b):
+            if b[1] == 0 or not (0 < int(b[0]) <= stride):
+                return None, 0
+            g = int(b[0])
+            arr = lambda i: b[16 + i * stride:16 + i * stride + g].astype(np.int64)   # noqa: E731
+            starts, ends = arr(0), arr(1)
+            t0 = int(starts.min())
+            us = lambda v: (int(v) - t0) / 1e3   # noqa: E731
+            out = {"grid": g, "cta_start_spread_us": us(starts.max()), "cta_start_p90_us": us(np.percentile(starts, 90)),
+                   "scan_end_first_us": us(ends.min()),
+                   "scan_end_median_us": us(np.median(ends)), "scan_end_last_us": us(ends.max()), "ticket_us": us(b[1]),
+                   "local_topk_us": us(b[2]), "done_us": us(b[5])}
+            tb, te = arr(2), arr(3)
+            if tb.min() > 0 and te.min() > 0:
+                out["transition_wait_median_us"] = float(np.median(te - tb)) / 1e3
+                out["transition_wait_max_us"] = float((te - tb).max()) / 1e3
+            if b[13]:
+                out["phase_b_offers"], out["phase_b_inserts"], out["transition_keys"] = int(b[11]), int(b[12]), int(b[13])
+            if b[3] and b[4]:
+                out["pushed_us"], out["peers_seen_us"] = us(b[3]), us(b[4])
+            if raw:
+                out["raw"] = {"start": (starts - t0) / 1e3, "end": (ends - t0) / 1e3, "trans_begin": (tb - t0) / 1e3,
+                              "trans_end": (te - t0) / 1e3, "static_end": (arr(4) - t0) / 1e3, "smid": arr(5)}
+            return out, t0
+
+        out, t0 = parse(buf[:half])
+        if out is not None and previous:
+            prev, p0 = parse(buf[half:])
+            if prev is not None:
+                out["previous"] = prev
+                out["period_us"] = (t0 - p0) / 1e3
         return out
 
     def stats(self) -> Dict[str, Any]:

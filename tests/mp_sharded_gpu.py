@@ -13,6 +13,56 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 
+def overlapped_stable_calls(pkg, ShardedFlatIPIndex, rank, world, local, dev):
+    """B2S_SEARCH_STABLE_QUERIES on a sharded index: the scan of call i+1 overlaps the NVLink exchange of call i.
+    300 back-to-back calls must equal the same calls issued one at a time, on every rank, and a torch fp32
+    reference (shard-local top-k, gathered, merged) on the rows the index holds."""
+    from semantic_search_kd_b200.sharded import shard_range
+    n_per = 700_000                                   # large enough for the cascade select
+    total = n_per * world
+    lo, hi = shard_range(total, world, rank)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + rank)
+    Xl = torch.randn((hi - lo, 384), generator=g, device=dev)
+    Xl = Xl / Xl.norm(dim=1, keepdim=True)
+    loc = pkg.FlatIPIndex(384, metric="inner_product", device=local)
+    loc.add(Xl)
+    idx = ShardedFlatIPIndex(384, metric="inner_product", local_index=loc, exchange="peer")
+    idx.local.set_id_offset(lo)
+    idx.n_total, idx.range = total, (lo, hi)
+    g.manual_seed(55)                                 # same queries on every rank
+    Q = torch.randn((300, 384), generator=g, device=dev)
+    Q = (Q / Q.norm(dim=1, keepdim=True)).contiguous()
+    ks = [(10, 10, 10, 100, 1, 16)[i % 6] for i in range(300)]
+    serial = []
+    for i, k in enumerate(ks):
+        s, ids = idx.search_device(Q[i:i + 1], k)
+        torch.cuda.synchronize()
+        serial.append((s.clone(), ids.clone()))
+    dist.barrier()
+    outs = [idx.search_device(Q[i:i + 1], k, stable_queries=True) for i, k in enumerate(ks)]
+    torch.cuda.synchronize()
+    assert idx._ex_ready and idx.exchange_status() == 0
+    for i, ((s, ids), (rs, ri)) in enumerate(zip(outs, serial)):
+        assert torch.equal(ids, ri) and torch.equal(s, rs), ("stable != serial", i, ks[i], rank)
+    # torch fp32 reference on the bf16 rows, 24 of the k = 10 calls
+    Xb = Xl.to(torch.bfloat16).float()
+    sel = [i for i, k in enumerate(ks) if k == 10][:24]
+    ls, li = torch.topk(Q[sel] @ Xb.T, 10, dim=1)
+    gs = [torch.empty_like(ls) for _ in range(world)]
+    gi = [torch.empty_like(li) for _ in range(world)]
+    dist.all_gather(gs, ls.contiguous())
+    dist.all_gather(gi, (li + lo).contiguous())
+    cs, ci = torch.cat(gs, dim=1), torch.cat(gi, dim=1)
+    ts, pick = torch.topk(cs, 10, dim=1)
+    ref_i = torch.gather(ci, 1, pick)
+    for j, i in enumerate(sel):
+        assert torch.equal(outs[i][1][0], ref_i[j]), ("stable != torch reference", i, rank)
+        assert torch.allclose(outs[i][0][0], ts[j], atol=2e-5)
+    dist.barrier()
+    loc.close()
+
+
 def main():
     import semantic_search_kd_b200 as pkg
     from semantic_search_kd_b200.sharded import ShardedFlatIPIndex
@@ -25,7 +75,7 @@ def main():
     n = 50001
     X = unit_rows(n, 384, 11)
     X[n // 2 + 3] = X[17]
-    for nq, k in ((1, 10), (7, 10), (200, 10), (300, 100)):
+    for nq, k in ((1, 10), (7, 10), (200, 10), (300, 100), (3, 1000)):
         Q = unit_rows(nq, 384, 300 + nq)
         Dr, Ir = orc.flat_ip_topk(X, Q, k)
         res = {}
@@ -51,6 +101,7 @@ def main():
         t0 = t.clone()
         dist.broadcast(t0, 0)
         assert torch.equal(t, t0)
+    overlapped_stable_calls(pkg, ShardedFlatIPIndex, rank, world, local, dev)
     dist.barrier()
     if rank == 0:
         print("SHARDED_OK", world)

@@ -32,6 +32,7 @@ def _emulated_ranks(pkg, X, world, path):
         idx.add(X[lo:hi]) if hi > lo else idx._ensure()
         idx.set_id_offset(lo)
         rc = L.b2s_exchange_create(idx._h, world, r, 1 << 20, 4096, None)
+        idx.set_option("exchange_timeout_ms", 2000)
         assert rc == 0, pkg._lib.last_error()
         ranks.append(idx)
     ptrs = (ctypes.c_void_p * world)(*[L.b2s_exchange_local(i._h) for i in ranks])
@@ -41,7 +42,8 @@ def _emulated_ranks(pkg, X, world, path):
 
 
 @pytest.mark.parametrize("world,n,nq,k,path", [(2, 20000, 1, 10, 1), (3, 20001, 5, 10, 1), (4, 30000, 70, 100, 2),
-                                               (8, 5000, 200, 10, 2), (3, 2, 4, 10, 1), (2, 9000, 300, 7, 0)])
+                                               (8, 5000, 200, 10, 2), (3, 2, 4, 10, 1), (2, 9000, 300, 7, 0),
+                                               (8, 40000, 3, 1000, 2), (5, 30000, 2, 1000, 0)])   # world * k > 4096: run merge by binary search
 def test_emulated_ranks_two_phase(oracle, world, n, nq, k, path):
     import torch
     import semantic_search_kd_b200 as pkg

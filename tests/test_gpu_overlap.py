@@ -1,0 +1,164 @@
+"""GPU: consecutive searches of one handle that are allowed to overlap on the device.
+
+  * B2S_SEARCH_STABLE_QUERIES: the scan of call i+1 runs while the tail of call i (top-k read-out, on a sharded
+    index the NVLink exchange) is still in flight -- the two control sets of the scan kernel, their epoch
+    words and the one remaining grid dependency (scan_topk.cuh) must give bit-identical answers to the same
+    calls issued one at a time, for hundreds of calls in a row, with k switching between the cascade select
+    (k <= 16), the per-CTA lists (k > 16) and the tensor kernel in between.
+  * searches of one handle issued on DIFFERENT streams never overlap (the handle's workspaces are shared): the
+    event guard of b2s_search_device orders them.
+  * a search captured into a CUDA graph takes no part in the epoch protocol and may be replayed between live
+    overlapped calls.
+The shard is large enough (700k rows >= cascade_min_units iterations per warp) for the cascade select.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+N, D = 700_000, 384
+
+
+@pytest.fixture(scope="module")
+def big():
+    import torch
+    import semantic_search_kd_b200 as pkg
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(77)
+    X = torch.randn((N, D), generator=g, device=dev)
+    X = X / X.norm(dim=1, keepdim=True)
+    idx = pkg.FlatIPIndex(D, metric="inner_product", device=0)
+    idx.add(X)
+    Q = torch.randn((512, D), generator=g, device=dev)
+    Q = (Q / Q.norm(dim=1, keepdim=True)).contiguous()
+    torch.cuda.synchronize()
+    yield pkg, idx, X, Q, dev
+    idx.close()
+
+
+def _serial(idx, Q, ks):
+    import torch
+    outs = []
+    for i, k in enumerate(ks):
+        s, ids = idx.search_device(Q[i:i + 1], k)
+        torch.cuda.synchronize()
+        outs.append((s.clone(), ids.clone()))
+    return outs
+
+
+def test_cascade_select_matches_torch_reference(big):
+    """The cascade select (k <= 16 on a large shard) against torch fp32 on the bf16 rows the index holds."""
+    import torch
+    pkg, idx, X, Q, dev = big
+    Xb = X.to(torch.bfloat16).float()
+    for k in (1, 10, 16):
+        s, ids = idx.search_device(Q[:1], k)
+        torch.cuda.synchronize()
+        ref_s, ref_i = torch.topk(Q[:1] @ Xb.T, k, dim=1)
+        assert torch.equal(ids, ref_i), (k, ids, ref_i)
+        assert torch.allclose(s, ref_s, atol=2e-5)
+    s2, ids2 = idx.search_device(Q[:2], 10)           # two queries in one launch
+    torch.cuda.synchronize()
+    ref_s, ref_i = torch.topk(Q[:2] @ Xb.T, 10, dim=1)
+    assert torch.equal(ids2, ref_i) and torch.allclose(s2, ref_s, atol=2e-5)
+
+
+@pytest.mark.parametrize("pattern", ["k10", "mixed"])
+def test_stable_queries_overlap_is_bit_identical(big, pattern):
+    import torch
+    pkg, idx, X, Q, dev = big
+    n = 300
+    ks = [10] * n if pattern == "k10" else [(10, 100, 3, 16, 17, 1)[i % 6] for i in range(n)]
+    ref = _serial(idx, Q, ks)
+    outs = []
+    for i, k in enumerate(ks):                       # back to back, no synchronisation in between
+        outs.append(idx.search_device(Q[i:i + 1], k, stable_queries=True))
+        if pattern == "mixed" and i % 50 == 25:      # a tensor-path call of the same handle in the chain
+            idx.search_device(Q[:8], 10)
+    torch.cuda.synchronize()
+    for i, ((s, ids), (rs, ri)) in enumerate(zip(outs, ref)):
+        assert torch.equal(ids, ri), (i, ks[i])
+        assert torch.equal(s, rs), (i, ks[i])
+
+
+def test_stable_queries_option_pdl2_and_host_calls_interleaved(big):
+    """Option pdl=2 (every device call treated as stable) with host-buffer calls in between."""
+    import torch
+    pkg, idx, X, Q, dev = big
+    Qh = Q.cpu().numpy()
+    ref = _serial(idx, Q, [10] * 40)
+    idx.set_option("pdl", 2)
+    try:
+        outs = []
+        for i in range(40):
+            outs.append(idx.search_device(Q[i:i + 1], 10))
+            if i % 7 == 3:
+                sh, ih = idx.search(Qh[i:i + 1], 10)   # private stream + stream guard
+                assert np.array_equal(ih, ref[i][1].cpu().numpy())
+        torch.cuda.synchronize()
+        for (s, ids), (rs, ri) in zip(outs, ref):
+            assert torch.equal(ids, ri) and torch.equal(s, rs)
+    finally:
+        idx.set_option("pdl", 1)
+
+
+def test_searches_on_different_streams_do_not_overlap(big):
+    """Two torch streams alternate on one handle, one of them behind a long-running kernel: without the event
+    guard the second stream's search would run concurrently with the first one's and share its workspaces."""
+    import torch
+    pkg, idx, X, Q, dev = big
+    ref = _serial(idx, Q, [10] * 64)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    s1.wait_stream(torch.cuda.current_stream())
+    s2.wait_stream(torch.cuda.current_stream())
+    outs = []
+    for i in range(64):
+        st = s1 if i % 2 == 0 else s2
+        with torch.cuda.stream(st):
+            outs.append(idx.search_device(Q[i:i + 1], 10, stable_queries=(i % 3 == 0)))
+    torch.cuda.synchronize()
+    for i, ((s, ids), (rs, ri)) in enumerate(zip(outs, ref)):
+        assert torch.equal(ids, ri) and torch.equal(s, rs), i
+
+
+def test_graph_replay_between_overlapped_calls(big):
+    import torch
+    pkg, idx, X, Q, dev = big
+    ref = _serial(idx, Q, [10] * 30)
+    q = Q[100:101].clone()
+    out = (torch.empty((1, 10), dtype=torch.float32, device=dev), torch.empty((1, 10), dtype=torch.int64, device=dev))
+    idx.search_device(q, 10, out=out)
+    torch.cuda.synchronize()
+    want = (out[0].clone(), out[1].clone())
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            idx.search_device(q, 10, out=out)
+    outs = []
+    for i in range(30):
+        outs.append(idx.search_device(Q[i:i + 1], 10, stable_queries=True))
+        if i % 10 == 5:
+            torch.cuda.synchronize()                 # the graph is ordered by whoever replays it
+            out[0].zero_()
+            g.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(out[1], want[1]) and torch.equal(out[0], want[0])
+    torch.cuda.synchronize()
+    for (s, ids), (rs, ri) in zip(outs, ref):
+        assert torch.equal(ids, ri) and torch.equal(s, rs)
+
+
+def test_trace_reports_both_launches(big):
+    import torch
+    pkg, idx, X, Q, dev = big
+    idx.set_option("trace", 1)
+    try:
+        for i in range(6):
+            idx.search_device(Q[i:i + 1], 10, stable_queries=True)
+        t = idx.read_trace(previous=True)
+    finally:
+        idx.set_option("trace", 0)
+    assert t is not None and t["grid"] > 0 and t["done_us"] > t["scan_end_first_us"] > 0
+    assert "previous" in t and 0 < t["period_us"] < 10_000
