@@ -457,6 +457,21 @@ def run_ours(args):
         except Exception as e:
             extras["cfg_ance"] = {"error": repr(e)}
         try:
+            # the same sweep with the corpus replicated (6.8 GB per GPU) and the QUERIES sharded: no exchange
+            full = pkg.FlatIPIndex(DIM, metric="inner_product", device=local_rank)
+            full.reserve(args.rows)
+            for blk in make_rows(torch, 0, args.rows, dev):
+                full.add(blk)
+            torch.cuda.synchronize()
+            extras["cfg_ance_query_sharded"] = bx.cfg_ance_report(torch, dist, pkg, full, full, DIM, args.rows, world, rank,
+                                                                  local_rank, dev, nq_total=args.ance_queries * max(1, world // 2),
+                                                                  mode="query_sharded")
+            full.close()
+            del full
+            torch.cuda.empty_cache()
+        except Exception as e:
+            extras["cfg_ance_query_sharded"] = {"error": repr(e)}
+        try:
             extras["cfg_100m"] = bx.cfg_100m_report(torch, dist, pkg, make_rows, DIM, world, rank, local_rank, dev,
                                                     rows=args.rows_100m)
         except Exception as e:

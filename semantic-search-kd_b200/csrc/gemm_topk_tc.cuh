@@ -395,11 +395,18 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
             if (warp == 4 && lane == 0) *(volatile int*)s_cur_qb = qb;   // tell the bound-updater warp
             const int t0 = chunk * p.chunk_tiles;
             const int t1 = min(t0 + p.chunk_tiles, p.tiles_total);
+            // the query's shared bound (other CTA pairs raise it) is fetched ONE TILE AHEAD: when the epilogue is
+            // the busy side of the pipeline the accumulator is already waiting, and an L2 round trip per tile in
+            // front of the first compare was the largest single stall of the kernel at k = 1000 (ncu, r02)
+            unsigned g_next = 0u;
+            if constexpr (!PREPASS) {
+                if (shared_thr) g_next = ldcg_pinned_u32(gthr_q);
+            }
             for (int t = t0; t < t1; ++t) {
-                // the query's shared bound (other CTA pairs raise it); the load flies during the wait
                 unsigned g = 0u;
                 if constexpr (!PREPASS) {
-                    if (shared_thr) g = __ldcg(gthr_q);
+                    g = g_next;
+                    if (shared_thr) g_next = ldcg_pinned_u32(gthr_q);   // for the next tile
                 }
                 ptx::mbar_wait(&acc_full[acc], acc_phase);
                 ptx::tc_fence_after();

@@ -84,6 +84,14 @@ __device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// L2 load pinned in program order (volatile asm): issued where it is written, so that a value wanted one loop
+// iteration later is in flight for a whole iteration instead of being sunk to its use by the compiler
+__device__ __forceinline__ unsigned ldcg_pinned_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 // nanoseconds of the GPU-wide timer (comparable across SMs; ~32 ns granularity): option "trace" stamps
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;

@@ -295,24 +295,42 @@ def cfg_100m_report(torch, dist, pkg, make_rows, dim, world, rank, local_rank, d
 
 
 def cfg_ance_report(torch, dist, pkg, idx, local, dim, rows, world, rank, local_rank, dev,
-                    nq_total=32768, top_k=200, batch=4096, margin=0.1):
-    """BASELINE configs[2], bounded: nq_total (of the 500k) queries x the 8.8M corpus this run already holds
-    row-sharded, exact top-(200 + 1 positive), positive scoring, ANCE margin filter (csrc/ance_filter.cuh)."""
+                    nq_total=32768, top_k=200, batch=4096, margin=0.1, mode="corpus_sharded"):
+    """BASELINE configs[2], bounded: nq_total (of the 500k) queries x the 8.8M corpus, exact top-(200 + 1 positive),
+    positive scoring, ANCE margin filter (csrc/ance_filter.cuh).
+      mode "corpus_sharded": the corpus this run already holds row-sharded; every rank sees every query batch, the
+                             candidates are exchanged over NVLink inside the merge kernels;
+      mode "query_sharded":  `idx` = `local` holds the WHOLE corpus on every GPU (6.8 GB of 180), every rank mines its
+                             own 1/world of the queries -- no exchange at all (the better layout for this workload)."""
     pk = measured_peaks()
     L = pkg._lib.lib()
+    from semantic_search_kd_b200.sharded import shard_range
+    if mode == "query_sharded":
+        qlo, qhi = shard_range(nq_total, world, rank)
+    else:
+        qlo, qhi = 0, nq_total
+    phases = {"queries": 0.0, "search": 0.0, "positives": 0.0, "filter": 0.0}
 
-    def process(b0):
-        nb = min(batch, nq_total - b0)
+    def process(b0, ev=None):
+        nb = min(batch, qhi - b0)
+        if ev:
+            ev[0].record()
         Q = unit_queries(torch, nb, dim, dev, 1000 + b0)
         pos = ((torch.arange(b0, b0 + nb, device=dev, dtype=torch.int64) * 7919) % rows).view(nb, 1)
+        if ev:
+            ev[1].record()
         s, i = idx.search_device(Q, top_k + 1)
+        if ev:
+            ev[2].record()
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         ps = torch.empty((nb, 1), dtype=torch.float32, device=dev)
         rc = L.b2s_score_rows_device(local._h, ctypes.c_void_p(Q.data_ptr()), 0, 1, nb, ctypes.c_void_p(pos.data_ptr()), 1,
                                      ctypes.c_void_p(ps.data_ptr()), stream)
         assert rc == 0, pkg._lib.last_error()
-        if world > 1:   # the positive's row lives on one shard (-FLT_MAX elsewhere)
+        if world > 1 and mode == "corpus_sharded":   # the positive's row lives on one shard (-FLT_MAX elsewhere)
             dist.all_reduce(ps, op=dist.ReduceOp.MAX)
+        if ev:
+            ev[3].record()
         out_i = torch.empty((nb, top_k), dtype=torch.int64, device=dev)
         out_s = torch.empty((nb, top_k), dtype=torch.float32, device=dev)
         cnt = torch.empty((nb,), dtype=torch.int32, device=dev)
@@ -321,29 +339,43 @@ def cfg_ance_report(torch, dist, pkg, idx, local, dim, rows, world, rank, local_
                                       top_k, ctypes.c_void_p(out_i.data_ptr()), ctypes.c_void_p(out_s.data_ptr()),
                                       ctypes.c_void_p(cnt.data_ptr()), stream)
         assert rc == 0, pkg._lib.last_error()
+        if ev:
+            ev[4].record()
         return cnt
 
-    process(0)
+    process(qlo)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for b0 in range(0, nq_total, batch):
+    for b0 in range(qlo, qhi, batch):
         cnt = process(b0)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    # the same loop once more with events between the phases (untimed: where a batch's time goes)
+    n_b = 0
+    for b0 in range(qlo, qhi, batch):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        process(b0, ev)
+        torch.cuda.synchronize()
+        for name, a, b in (("queries", 0, 1), ("search", 1, 2), ("positives", 2, 3), ("filter", 3, 4)):
+            phases[name] += ev[a].elapsed_time(ev[b])
+        n_b += 1
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     flops_gpu = 2.0 * nq_total * rows * dim / world
     tfs = flops_gpu / (ms * 1e-3) / 1e12
-    return {"workload": f"BASELINE configs[2] (bounded sample): ANCE sweep, {nq_total} of the 500k queries x {rows:,} rows "
-                        f"row-sharded over {world} GPU(s), top-{top_k} negatives, margin {margin}, batches of {batch}",
-            "seconds": ms * 1e-3, "queries_per_s": nq_total / (ms * 1e-3), "full_500k_sweep_s_at_this_rate": 500_000 / (nq_total / (ms * 1e-3)),
+    return {"workload": f"BASELINE configs[2] (bounded sample): ANCE sweep, {nq_total} of the 500k queries x {rows:,} rows, "
+                        f"{mode.replace('_', '-')} over {world} GPU(s), top-{top_k} negatives, margin {margin}, batches of {batch}",
+            "mode": mode, "seconds": ms * 1e-3, "queries_per_s": nq_total / (ms * 1e-3),
+            "full_500k_sweep_s_at_this_rate": 500_000 / (nq_total / (ms * 1e-3)),
             "tflops_per_gpu": tfs, "frac_of_bf16_sustained_peak": tfs / pk["bf16_tflops_sustained"],
             "frac_of_bf16_burst_peak": tfs / pk["bf16_tflops"],
-            "includes": "query generation, exact top-201 search + candidate exchange, positive scoring, ANCE margin filter",
+            "includes": "query generation, exact top-201 search" + (" + candidate exchange" if mode == "corpus_sharded" and world > 1 else "")
+                        + ", positive scoring, ANCE margin filter",
+            "ms_per_batch_by_phase_rank0": {k: round(v / max(1, n_b), 4) for k, v in phases.items()},
             "negatives_last_batch_mean": float(cnt.float().mean().item()), "exchange": getattr(idx, "exchange", None)}
