@@ -16,6 +16,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200search.h"
@@ -121,6 +122,9 @@ struct b2s_index {
     // workspace
     DevBuf ws_lists, ws_counts, ws_thr, ws_gmax, ws_hist, ws_hcfg, ws_rs_scores, ws_rs_ids, ws_seed, ws_qf32, ws_qbf16, ws_io_q, ws_io_ids, ws_tmp;
     void* pin_q = nullptr;
+    // host ingest (b2s_add_* with host rows): two pinned staging buffers + their "DMA done" events
+    void* pin_in[2] = {nullptr, nullptr};
+    cudaEvent_t pin_in_ev[2] = {nullptr, nullptr};
     void* pin_out = nullptr;
     size_t pin_q_bytes = 0, pin_out_bytes = 0;
     cudaStream_t stream = nullptr;
@@ -763,6 +767,10 @@ B2S_API int b2s_destroy(b2s_index* idx) {
     if (idx->trace_buf) cudaFree(idx->trace_buf);
     if (idx->xs_event) cudaEventDestroy(idx->xs_event);
     if (idx->pin_q) cudaFreeHost(idx->pin_q);
+    for (int i = 0; i < 2; ++i) {
+        if (idx->pin_in[i]) cudaFreeHost(idx->pin_in[i]);
+        if (idx->pin_in_ev[i]) cudaEventDestroy(idx->pin_in_ev[i]);
+    }
     if (idx->pin_out) cudaFreeHost(idx->pin_out);
     if (idx->ring) {
         for (int i = 0; i < 4 * kTimingSlots; ++i)
@@ -783,6 +791,29 @@ B2S_API int b2s_reserve(b2s_index* idx, int64_t n_rows) {
     return grow_rows(idx, n_rows);
 }
 
+// Host rows reach the device through two pinned staging buffers: while the copy engine moves chunk c and the
+// convert kernel runs, a few host threads already copy chunk c+1 into the other buffer (a pageable
+// cudaMemcpyAsync would serialise the staging copy, the DMA and the kernel, chunk after chunk).
+constexpr size_t kIngestChunkBytes = (size_t)64 << 20;
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int nt = (int)std::min<size_t>(std::min(8u, hw), bytes >> 22);   // >= 4 MB per thread
+    if (nt <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
+    for (int t = 1; t < nt; ++t) {
+        const size_t off = (size_t)t * per;
+        if (off >= bytes) break;
+        const size_t len = std::min(per, bytes - off);
+        th.emplace_back([=] { memcpy((unsigned char*)dst + off, (const unsigned char*)src + off, len); });
+    }
+    memcpy(dst, src, std::min(per, bytes));
+    for (auto& t : th) t.join();
+}
+
 static int add_impl(b2s_index* idx, const void* rows, int64_t n, int is_device, bool is_bf16, bool prepared = false) {
     if (!idx) return fail(B2S_ERR_INVALID, "null index");
     if (n < 0) return fail(B2S_ERR_INVALID, "n < 0");
@@ -796,15 +827,36 @@ static int add_impl(b2s_index* idx, const void* rows, int64_t n, int is_device, 
     const int dim = idx->dim;
     const size_t esz = is_bf16 ? 2 : 4;
     const bool normalize = idx->metric == B2S_METRIC_COSINE && !prepared;
-    const int64_t chunk_rows = std::max<int64_t>(1, ((int64_t)256 << 20) / ((int64_t)dim * (int64_t)esz));
-    for (int64_t r0 = 0; r0 < n; r0 += chunk_rows) {
+    const size_t chunk_bytes = is_device ? ((size_t)256 << 20) : kIngestChunkBytes;
+    const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)chunk_bytes / ((int64_t)dim * (int64_t)esz));
+    const size_t stage_bytes = (size_t)chunk_rows * dim * esz;
+    if (!is_device) {
+        if ((rc = idx->ws_tmp.ensure(2 * stage_bytes)) != B2S_OK) return rc;   // two device halves as well
+        for (int i = 0; i < 2; ++i) {
+            if (!idx->pin_in[i]) {
+                // (stage_bytes <= kIngestChunkBytes for either element size: chunk_rows is a floor)
+                if (cudaHostAlloc(&idx->pin_in[i], std::max(kIngestChunkBytes, (size_t)dim * 4), cudaHostAllocDefault) != cudaSuccess) {
+                    cudaGetLastError();
+                    return fail(B2S_ERR_NOMEM, "cudaHostAlloc failed (host ingest staging)");
+                }
+            }
+            if (!idx->pin_in_ev[i]) CUDA_TRY(cudaEventCreateWithFlags(&idx->pin_in_ev[i], cudaEventDisableTiming));
+        }
+    }
+    int64_t chunk_no = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += chunk_rows, ++chunk_no) {
         const int64_t rn = std::min<int64_t>(chunk_rows, n - r0);
         const unsigned char* src = reinterpret_cast<const unsigned char*>(rows) + (size_t)r0 * dim * esz;
         const void* dsrc = src;
         if (!is_device) {
-            if ((rc = idx->ws_tmp.ensure((size_t)rn * dim * esz)) != B2S_OK) return rc;
-            CUDA_TRY(cudaMemcpyAsync(idx->ws_tmp.p, src, (size_t)rn * dim * esz, cudaMemcpyHostToDevice, idx->stream));
-            dsrc = idx->ws_tmp.p;
+            const int b = (int)(chunk_no & 1);
+            const size_t bytes = (size_t)rn * dim * esz;
+            if (chunk_no >= 2) CUDA_TRY(cudaEventSynchronize(idx->pin_in_ev[b]));   // its previous DMA has finished
+            parallel_memcpy(idx->pin_in[b], src, bytes);
+            unsigned char* dtmp = reinterpret_cast<unsigned char*>(idx->ws_tmp.p) + (size_t)b * stage_bytes;
+            CUDA_TRY(cudaMemcpyAsync(dtmp, idx->pin_in[b], bytes, cudaMemcpyHostToDevice, idx->stream));
+            CUDA_TRY(cudaEventRecord(idx->pin_in_ev[b], idx->stream));
+            dsrc = dtmp;
         }
         __nv_bfloat16* dst = idx->rows + (size_t)(idx->n + r0) * dim;
         const int warps = 8;
@@ -837,8 +889,9 @@ static int add_impl(b2s_index* idx, const void* rows, int64_t n, int is_device, 
                 }
             }
         }
-        CUDA_TRY(cudaStreamSynchronize(idx->stream));
+        if (is_device) CUDA_TRY(cudaStreamSynchronize(idx->stream));   // the caller's buffer may be reused right away
     }
+    CUDA_TRY(cudaStreamSynchronize(idx->stream));
     idx->n += n;
 #ifndef B2S_NO_TENSOR_PATH
     idx->tc.corpus_map_valid = false;

@@ -443,23 +443,55 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_corpus, const __grid_co
                         }
                         if (fmaxf(fmaxf(g8[0], g8[1]), fmaxf(g8[2], g8[3])) >= thr) {
                             const uint32_t row_c = row_base + (uint32_t)(c * 32);
+                            // one survivor: append, count, keep the list bounded
+                            auto keep = [&](float sc, uint32_t row) {
+                                const u64 key = make_key(sc, row);
+                                if (key > tk && row < p.n_rows) {
+                                    my_list[cnt++] = key;
+                                    if (shared_thr) hist_count(hist_q, (uint32_t)(key >> 32), hc);
+                                    if (cnt == p.cap) {
+                                        tk = list_keep_top_k(my_list, cnt, p.k);
+                                        thr = key_score(tk);
+                                        cnt = p.k;
+                                    }
+                                }
+                            };
+                            // Common case, branch-free up to the append: exactly ONE of this lane's four 8-row groups
+                            // reaches the threshold and exactly one of its rows does -- that row is the group maximum.
+                            // (The slow path is entered by a third of the warp-chunks at k = 1000; walking 4 x 8
+                            // unrolled per-row bodies cost ~260 warp instructions per entry and made the slowest of a
+                            // pair's 16 epilogue warps pace the MMA pipe: ncu, profiles/r02_k2_ncu_summary.md.)
+                            const bool h0 = g8[0] >= thr, h1 = g8[1] >= thr, h2 = g8[2] >= thr, h3 = g8[3] >= thr;
+                            bool handled = false;
+                            if ((int)h0 + (int)h1 + (int)h2 + (int)h3 == 1) {
+                                float w8[8];
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                if (g8[g] >= thr) {
+                                for (int i = 0; i < 8; ++i) {
+                                    const float a = h0 ? v[i] : v[8 + i];
+                                    const float b = h2 ? v[16 + i] : v[24 + i];
+                                    w8[i] = (h0 || h1) ? a : b;
+                                }
+                                int n_hit = 0, idx = 0;
 #pragma unroll
-                                    for (int j = 8 * g; j < 8 * g + 8; ++j) {
-                                        if (v[j] >= thr) {
-                                            const uint32_t row = row_c + (uint32_t)j;
-                                            const u64 key = make_key(v[j], row);
-                                            if (key > tk && row < p.n_rows) {
-                                                my_list[cnt++] = key;
-                                                if (shared_thr) hist_count(hist_q, (uint32_t)(key >> 32), hc);
-                                                if (cnt == p.cap) {
-                                                    tk = list_keep_top_k(my_list, cnt, p.k);
-                                                    thr = key_score(tk);
-                                                    cnt = p.k;
-                                                }
-                                            }
+                                for (int i = 7; i >= 0; --i) {
+                                    const bool hit = w8[i] >= thr;
+                                    n_hit += hit ? 1 : 0;
+                                    idx = hit ? i : idx;
+                                }
+                                if (n_hit == 1) {
+                                    const int gi = h0 ? 0 : (h1 ? 1 : (h2 ? 2 : 3));
+                                    const float sc = h0 ? g8[0] : (h1 ? g8[1] : (h2 ? g8[2] : g8[3]));
+                                    keep(sc, row_c + (uint32_t)(gi * 8 + idx));
+                                    handled = true;
+                                }
+                            }
+                            if (!handled) {   // several survivors in this lane's chunk: walk the groups that hold one
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {
+                                    if (g8[g] >= thr) {
+#pragma unroll
+                                        for (int j = 8 * g; j < 8 * g + 8; ++j) {
+                                            if (v[j] >= thr) keep(v[j], row_c + (uint32_t)j);
                                         }
                                     }
                                 }
