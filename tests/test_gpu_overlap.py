@@ -162,3 +162,17 @@ def test_trace_reports_both_launches(big):
         idx.set_option("trace", 0)
     assert t is not None and t["grid"] > 0 and t["done_us"] > t["scan_end_first_us"] > 0
     assert "previous" in t and 0 < t["period_us"] < 10_000
+
+
+def test_every_kernel_family_small_shapes():
+    """tools/sanitize_smoke.py (written for compute-sanitizer, which this pool keeps closed) as a plain run: every
+    kernel family on tiny shapes, including the cascade select forced onto a 140k-row shard (cascade_min_units = 4),
+    both transition variants, overlapped launches with the trace on."""
+    import importlib.util
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    spec = importlib.util.spec_from_file_location("sanitize_smoke", root / "tools" / "sanitize_smoke.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main()

@@ -38,7 +38,10 @@ def main():
     assert (I[:, 0] == ref[:7].argmax(axis=1)).all()
     S, Dd = pkg.maxsim_topk(idx, Q[:9], 5, np.arange(len(X)) // 3)
     ids, sc, cnt = pkg.ANCEMiner(None, margin=0.05).mine_corpus(idx, Q[:9], [[int(i)] for i in ref[:9].argmax(axis=1)], top_k=20)
+    idx.close()
     L = pkg._lib.lib()
+    idx = pkg.FlatIPIndex(384, metric="inner_product")     # (the peer exchange refuses fp32 re-ranking)
+    idx.add(X)
     assert L.b2s_exchange_create(idx._h, 1, 0, 1 << 20, 4096, None) == 0
     ptrs = (ctypes.c_void_p * 1)(L.b2s_exchange_local(idx._h))
     assert L.b2s_exchange_connect(idx._h, ptrs, 1) == 0
@@ -49,6 +52,22 @@ def main():
                                     I2.ctypes.data_as(ctypes.c_void_p)) == 0
         assert (I2[:nq, 0] == ref[:nq].argmax(axis=1)).all()
     idx.close()
+    # cascade select + dynamic tail + overlapped (stable-query) launches + trace, on the smallest shard that takes them
+    Xc = unit(140_000, 3)
+    refc = Q[:12] @ Xc.T
+    idx = pkg.FlatIPIndex(384, metric="inner_product")
+    idx.set_option("cascade_min_units", 4)
+    idx.add(Xc)
+    dev = torch.device("cuda", 0)
+    Qd = torch.from_numpy(Q[:12]).to(dev)
+    for tm in (0, 1):
+        idx.set_option("transition_mode", tm)
+        idx.set_option("trace", tm)
+        outs = [idx.search_device(Qd[i:i + 1], (10, 16, 3)[i % 3], stable_queries=True) for i in range(12)]
+        torch.cuda.synchronize()
+        for i, (s_, i_) in enumerate(outs):
+            assert int(i_[0, 0]) == int(refc[i].argmax()), (tm, i)
+    idx.set_option("trace", 0)
     torch.cuda.synchronize()
     print("SANITIZE_SMOKE_OK")
 
