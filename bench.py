@@ -385,6 +385,12 @@ def run_ours(args):
     barrier()
     # ---- the timed region: exactly K steps, one kernel launch each, CUDA events on the launching stream ----
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        # The ranks leave the host barrier tens of microseconds apart -- visible when K = 20 steps are 2.5 ms.  One
+        # untimed search is enqueued in front of the start event: its candidate exchange makes every GPU reach the
+        # event within the same few microseconds.  The event sits between that kernel and step 1, so nothing of
+        # it overlaps the timed region (an event between two kernels switches their overlap off).
+        step_dev(args.warmup - 1)
     e0.record()
     for i in range(args.steps):
         step_dev(args.warmup + i)
@@ -490,11 +496,17 @@ def run_ours(args):
         achieved = local_bytes / (k_launch_ms * 1e-3) / 1e9
         traffic, traffic_src = None, None
         tp = ROOT / "profiles" / "traffic.json"
-        if tp.exists() and n_gpus == 1:
+        if tp.exists():
             try:
                 tj = json.loads(tp.read_text())
-                traffic = tj.get("scan_topk_kernel_dram_bytes_per_launch")
-                traffic_src = "static file profiles/traffic.json (one `ncu --set full` capture: %s), not measured in this run" % tj.get("source")
+                shard = tj.get("shard_%d_rows" % (hi - lo))   # the capture of this very shard size, if there is one
+                if n_gpus == 1 and args.rows == N_ROWS:
+                    traffic = tj.get("scan_topk_kernel_dram_bytes_per_launch")
+                elif shard:
+                    traffic = shard["dram_bytes_read"] + shard["dram_bytes_write"]
+                if traffic:
+                    traffic_src = ("static file profiles/traffic.json (one `ncu --set full` capture of this kernel on ONE GPU holding "
+                                   "a shard of this size: %s), not measured in this run" % tj.get("source"))
             except Exception:
                 traffic = None
         value = args.steps / (ms * 1e-3)
@@ -532,7 +544,7 @@ def run_ours(args):
                 "tail_breakdown_us": breakdown,
                 "parity": parity,
                 "gpu_launches": launches_per_step * args.steps,
-                "setup_searches": 32, "clocks": clk, "build_s": round(t_build, 2), "paths_agree": agree, "exchange_timeouts": ex_status}
+                "setup_searches": 32, "aligned_start": world > 1, "clocks": clk, "build_s": round(t_build, 2), "paths_agree": agree, "exchange_timeouts": ex_status}
         line.update(extras)
         if n_gpus == 1 and not args.no_batched:
             try:
