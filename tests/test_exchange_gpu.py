@@ -119,3 +119,30 @@ def test_multi_gpu_processes():
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "SHARDED_OK" in r.stdout
+
+
+def test_missing_peer_fails_the_call_instead_of_hanging():
+    """A rank whose peer never issues the call must get an ERROR after `exchange_timeout_ms`, not a hang and not
+    silent garbage: the kernel stores the call's sequence number into a mapped host word, the
+    host-buffer call that hit it returns B2S_ERR_CUDA, and so does every later sharded call on the handle."""
+    import time
+    import semantic_search_kd_b200 as pkg
+    L = pkg._lib.lib()
+    X, Q = unit_rows(5000, 384, 3), unit_rows(2, 384, 4)
+    ranks = _emulated_ranks(pkg, X, 2, 1)
+    for idx in ranks:
+        idx.set_option("exchange_timeout_ms", 50)
+    D = np.empty((1, 10), np.float32)
+    I = np.empty((1, 10), np.int64)
+    args = (Q.ctypes.data_as(ctypes.c_void_p), 1, 10, D.ctypes.data_as(ctypes.c_void_p), I.ctypes.data_as(ctypes.c_void_p))
+    t0 = time.perf_counter()
+    rc = L.b2s_search_sharded(ranks[0]._h, *args)          # rank 1 never calls
+    dt = time.perf_counter() - t0
+    assert rc == pkg._lib.B2S_ERR_CUDA, (rc, pkg._lib.last_error())
+    assert "timed out" in pkg._lib.last_error()
+    assert 0.02 < dt < 5.0, dt                             # one deadline for the whole call
+    assert L.b2s_exchange_status(ranks[0]._h) != 0
+    assert L.b2s_search_sharded(ranks[0]._h, *args) == pkg._lib.B2S_ERR_CUDA   # the handle stays failed: no silent reuse
+    assert L.b2s_search(ranks[0]._h, *args) == 0            # the plain (unsharded) search of the handle still works
+    for idx in ranks:
+        idx.close()
