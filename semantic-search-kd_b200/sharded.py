@@ -30,7 +30,7 @@ import numpy as np
 
 from . import _lib
 from .errors import IndexBuildError, IndexNotBuiltError
-from .index import FlatIPIndex, _check
+from .index import FlatIPIndex, _check, _small_call
 
 try:
     import torch
@@ -231,21 +231,28 @@ class ShardedFlatIPIndex:
         CUDA tensor in -> CUDA tensors out.  Every rank must call it with the same queries."""
         if torch is not None and isinstance(query_emb, torch.Tensor) and query_emb.is_cuda:
             return self.search_device(query_emb, k)
-        q = np.ascontiguousarray(np.asarray(query_emb, dtype=np.float32))
+        q = np.ascontiguousarray(query_emb, dtype=np.float32)
         if q.ndim == 1:
             q = q.reshape(1, -1)
-        dev = torch.device("cuda", self.local.device if self.local.device is not None else torch.cuda.current_device())
         nq = q.shape[0]
+        k = int(k)
+        peer = bool(nq and k and self.shard == "corpus" and self._peer_ok(nq, k))
+        if peer and self._ex_ready:     # the serving path: nothing below is needed
+            fast = _small_call(self, _lib.lib().b2s_search_sharded, "b2s_search_sharded", q, nq, k)
+            if fast is not None:
+                return fast
+        dev = torch.device("cuda", self.local.device if self.local.device is not None else torch.cuda.current_device())
         if self.shard == "queries":
             qd = torch.from_numpy(q).to(dev) if dev.type == "cuda" else torch.from_numpy(q)
             s, i = self._search_query_sharded(qd, k)
             return s.cpu().numpy(), i.cpu().numpy()
-        if nq and k and self._peer_ok(nq, k) and not self._ex_ready:
+        if peer and not self._ex_ready:
             self._connect_exchange(dev)
-        if nq and k and self._peer_ok(nq, k):
+            peer = self._peer_ok(nq, k)      # the connect may have fallen back to the all-gather path
+        if peer:
             scores = np.empty((nq, k), dtype=np.float32)
             ids = np.empty((nq, k), dtype=np.int64)
-            _check(_lib.lib().b2s_search_sharded(self.local._h, q.ctypes.data_as(ctypes.c_void_p), nq, int(k),
+            _check(_lib.lib().b2s_search_sharded(self.local._h, q.ctypes.data_as(ctypes.c_void_p), nq, k,
                                                  scores.ctypes.data_as(ctypes.c_void_p),
                                                  ids.ctypes.data_as(ctypes.c_void_p)), "b2s_search_sharded")
             return scores, ids
