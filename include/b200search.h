@@ -130,6 +130,9 @@ B2S_API int b2s_set_id_offset(b2s_index* idx, int64_t offset);
  *                 | 2 treat every device call as if B2S_SEARCH_STABLE_QUERIES were set (per handle)
  *   "pdl_early"   1 (default): the scan kernel triggers its dependent launch at its start, so the next search's
  *                 CTAs take over SM slots as this one's retire (no launch gap); 0 = after the scan
+ *   "host_spin"   1 (default): a host-buffer call of 1-2 queries waits on a completion word the kernel writes
+ *                 into mapped pinned memory after its last output (a few microseconds earlier than the stream
+ *                 reports completion); 0 = cudaStreamSynchronize
  *   "grid_spare"  CTA slots a fused-tail scan launch leaves free for its predecessor's last CTA (default 1)
  *   "cascade_min_units" static iterations per warp below which the cascade select is not used (default 32)
  *   "prefetch_iters" scan kernel: iterations per warp prefetched into L2 before the PDL wait (default 6)

@@ -13,11 +13,19 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <new>
 #include <string>
 #include <thread>
 #include <vector>
+
+#if defined(__x86_64__) || defined(__i386__)
+#include <immintrin.h>
+#define B2S_CPU_RELAX() _mm_pause()
+#else
+#define B2S_CPU_RELAX() ((void)0)
+#endif
 
 #include "../../include/b200search.h"
 #include "ance_filter.cuh"
@@ -176,7 +184,12 @@ struct b2s_index {
     bool last_stream_valid = false;
     cudaEvent_t xs_event = nullptr;
     const float* host_q = nullptr;      // host-buffer call in flight: its queries may ride in the kernel parameters
+    unsigned* host_flag = nullptr;      // ... and this mapped pinned word may be used as its completion flag
+    unsigned host_calls = 0;            // tiny host calls so far (flag values are never reused)
+    unsigned host_seq = 0;              // value the flag takes when the call in flight has written its outputs
+    bool host_flag_armed = false;       // a launch of the call in flight carries the flag
     int opt_fused_tail = 1;
+    int opt_host_spin = 1;              // tiny host calls: wait on the kernel's completion flag instead of the stream
     int opt_host_inline = 1;            // host-buffer calls of 1-2 queries: query in the kernel parameters, answer
                                         // written straight to pinned host memory (no copy-engine operations)
     int opt_exchange_ll = 1;            // fused exchange: tagged 8-byte words instead of payload + fence + flag
@@ -395,6 +408,11 @@ int search_scan(b2s_index* idx, const float* q_f32, int64_t nq, int k, float* ou
                               : nullptr;
                 // early trigger unless this launch would park its CTAs on a full-grid wait in the middle of the scan
                 p.early_trigger = (idx->opt_pdl_early && (!p.pdl_late_wait || cascade)) ? 1 : 0;
+                if (inline_q != nullptr && fuse_tail && idx->host_flag != nullptr && g0 + group >= cn && c0 + cn >= nq) {
+                    p.host_flag = idx->host_flag;   // the launch that writes the call's last outputs
+                    p.host_seq = idx->host_seq;
+                    idx->host_flag_armed = true;
+                }
                 if (inline_q != nullptr) {
                     p.use_inline = 1;
                     memcpy(p.q_inline, inline_q, (size_t)nq * idx->dim * sizeof(float));
@@ -994,6 +1012,8 @@ B2S_API int b2s_set_option(b2s_index* idx, const char* name, int64_t value) {
     } else if (s == "phase_a_stagger") {
         if (value < 1 || value > 4096) return fail(B2S_ERR_INVALID, "phase_a_stagger must be in [1, 4096]");
         idx->opt_phase_a_stagger = (int)value;
+    } else if (s == "host_spin") {
+        idx->opt_host_spin = value ? 1 : 0;
     } else if (s == "grid_spare") {
         if (value < 0 || value > 64) return fail(B2S_ERR_INVALID, "grid_spare must be in [0, 64]");
         idx->opt_grid_spare = (int)value;
@@ -1047,6 +1067,7 @@ B2S_API int64_t b2s_get_option(const b2s_index* idx, const char* name) {
     if (s == "trace") return idx->opt_trace;
     if (s == "pdl_early") return idx->opt_pdl_early;
     if (s == "grid_spare") return idx->opt_grid_spare;
+    if (s == "host_spin") return idx->opt_host_spin;
     if (s == "cascade_min_units") return idx->opt_cascade_min_units;
     if (s == "transition_mode") return idx->opt_transition_mode;
     if (s == "peek_every") return idx->opt_peek_every;
@@ -1101,10 +1122,16 @@ static int search_host(b2s_index* idx, const float* queries, int64_t nq, int k, 
                       nq <= scan_max_nq(idx->dim) && nq * idx->dim <= kScanInlineFloats && (sbytes + ibytes) <= 4096;
     unsigned char* po = nullptr;
     if (small) {
-        if ((rc = ensure_pinned(&idx->pin_out, &idx->pin_out_bytes, sbytes + ibytes)) != B2S_OK) return rc;
+        // (+ one 64-byte line behind the outputs: the completion flag of the tiny path)
+        if ((rc = ensure_pinned(&idx->pin_out, &idx->pin_out_bytes, ((sbytes + ibytes + 63) & ~(size_t)63) + 64)) != B2S_OK) return rc;
         po = reinterpret_cast<unsigned char*>(idx->pin_out);
     }
+    volatile unsigned* flag = nullptr;
     if (tiny) {
+        flag = reinterpret_cast<volatile unsigned*>(po + ((sbytes + ibytes + 63) & ~(size_t)63));
+        idx->host_flag = const_cast<unsigned*>(flag);
+        idx->host_seq = ++idx->host_calls;
+        idx->host_flag_armed = false;
         idx->host_q = queries;                                     // read at launch time, inside this call
         io_ids = reinterpret_cast<int64_t*>(po);                   // pinned host memory is device-accessible (UVA)
         io_scores = reinterpret_cast<float*>(po + ibytes);
@@ -1119,10 +1146,23 @@ static int search_host(b2s_index* idx, const float* queries, int64_t nq, int k, 
     rc = sharded ? search_sharded_impl(idx, idx->ws_io_q.p, B2S_DTYPE_F32, nq, k, io_scores, io_ids, idx->stream, 0)
                  : search_impl(idx, idx->ws_io_q.p, B2S_DTYPE_F32, nq, k, io_scores, io_ids, idx->stream);
     idx->host_q = nullptr;
+    idx->host_flag = nullptr;
     if (rc != B2S_OK) return rc;
     if (small) {
         if (!tiny) CUDA_TRY(cudaMemcpyAsync(po, idx->ws_io_ids.p, ibytes + sbytes, cudaMemcpyDeviceToHost, idx->stream));
-        CUDA_TRY(cudaStreamSynchronize(idx->stream));
+        bool seen = false;
+        if (tiny && idx->host_flag_armed && idx->opt_host_spin) {
+            // spin on the kernel's flag; every few hundred polls ask the stream, so that a failed or (impossibly)
+            // flag-less launch ends the wait through the ordinary synchronise below
+            const unsigned want = idx->host_seq;
+            for (unsigned spins = 1; !(seen = (*flag == want)); ++spins) {
+                if ((spins & 511u) == 0u && cudaStreamQuery(idx->stream) != cudaErrorNotReady) break;
+                B2S_CPU_RELAX();
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+            seen = seen || *flag == want;
+        }
+        if (!seen) CUDA_TRY(cudaStreamSynchronize(idx->stream));
         memcpy(out_ids, po, ibytes);
         memcpy(out_scores, po + ibytes, sbytes);
     } else {

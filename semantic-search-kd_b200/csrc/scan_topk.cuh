@@ -117,6 +117,11 @@ struct ScanParams {
     // Host-buffer searches of 1-2 queries: the query rides in the kernel parameters (constant bank) -- no
     // staging copy, no H2D operation in front of the kernel.
     int use_inline;
+    // Host-buffer calls whose outputs go straight to mapped pinned host memory: the last CTA stores host_seq here
+    // (system-scope fence first) after the last output, and the host thread, which is spinning on the word, has
+    // the answer a few microseconds before the grid has been torn down and the stream reports completion.
+    unsigned* host_flag;
+    unsigned host_seq;
     alignas(16) float q_inline[kScanInlineFloats];
 };
 
@@ -628,6 +633,10 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
             exchange_fused<kScanThreads>(p.ex, p.mp, sm.buf, kk, gq, tr);
         }
         __syncthreads();
+    }
+    if (p.host_flag != nullptr && tid == 0) {
+        __threadfence_system();                         // every output above (seen through the barrier) before the flag
+        *(volatile unsigned*)p.host_flag = p.host_seq;
     }
     if (tr) tr[5] = globaltimer_ns();
 }
