@@ -29,8 +29,10 @@
 //      slots' k-th key IS every CTA's threshold: a row that beats it is inserted straight away
 //      (~k ln(1/phase A fraction) insertions per query over the whole GPU).  When the scan ends the
 //      answer already sits sorted in the slots: the last CTA only reads k keys -- no merge.
-//      The switch from phase A to the slots is made warp by warp without a CTA barrier: the last warp
-//      of a CTA to get there flushes the CTA's list into the slots while the other seven stream on.
+//      The switch from phase A to the slots happens behind one CTA barrier: warp q sorts query q's list,
+//      adopts the better of its k-th key and the slots' k-th key, and walks the insertion chain while the
+//      other warps stream on (a barrier-free warp-by-warp switch exists as an A/B variant: no faster, and
+//      it sends 2.5x as many offers to the slots).
 //
 // Consecutive launches: the state launches share (done ticket, dynamic-tail counters, cascade slots)
 // exists TWICE (ScanCtl[2]) and is used alternately; the last CTA of a launch resets its set and
@@ -82,7 +84,7 @@ struct ScanParams {
                            // kernel reads early is produced by its predecessor: the PDL wait is deferred to
                            // the first point where state shared with the predecessor is touched (cascade:
                            // the phase A -> B transition; lists: before the dynamic tail / the write-out)
-    // Fused tail: the LAST CTA to finish (ticket from *done_counter) produces the final top-k itself -- no
+    // Fused tail: the LAST CTA to finish (ticket from ctl->done) produces the final top-k itself -- no
     // separate merge kernel, no kernel boundary.  1 = write the final top-k (mp.out_*); 2 = sharded
     // search: push to the peers, wait, merge (ex).
     int fused_tail;

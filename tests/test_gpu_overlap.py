@@ -176,3 +176,23 @@ def test_every_kernel_family_small_shapes():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     mod.main()
+
+
+def test_host_completion_flag_and_stream_wait_agree(big):
+    """Host-buffer calls of 1-2 queries: waiting on the kernel's completion word (default) and waiting on the stream
+    (option host_spin = 0) return the same bytes, call after call, also right after device-path calls."""
+    import torch
+    pkg, idx, X, Q, dev = big
+    Qh = Q.cpu().numpy()
+    want = []
+    idx.set_option("host_spin", 0)
+    try:
+        for i in range(24):
+            want.append(idx.search(Qh[i:i + 1 + (i % 2)], (10, 3, 16, 50)[i % 4]))
+    finally:
+        idx.set_option("host_spin", 1)
+    for i in range(24):
+        if i % 5 == 0:
+            idx.search_device(Q[i:i + 1], 10, stable_queries=True)       # something in flight on another stream
+        D, I = idx.search(Qh[i:i + 1 + (i % 2)], (10, 3, 16, 50)[i % 4])
+        assert np.array_equal(I, want[i][1]) and np.array_equal(D, want[i][0]), i
