@@ -52,6 +52,8 @@ constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kScanInlineFloats = 768;   // queries of a host call travel inside the kernel parameters (<= 3 KB)
 constexpr int kScanMaxNQ = 4;            // queries one launch holds in registers
 constexpr int kCascadeMaxK = 16;         // slots per query of the cascade select
+constexpr int kCascadeStormOffers = 12;  // offers to the slots one warp may make in phase B before its CTA falls back to lists
+constexpr unsigned kCascadeStormGrid = 1024u;   // ... and offers of the whole grid (random data: ~200 per search)
 constexpr int kWorkCounterStride = 32;   // words between the dynamic tail's ticket counters (one 128-byte line each)
 constexpr int kTraceWords = 16;          // header of the trace buffer, then kTraceArrays arrays of kTraceStride per-CTA stamps:
 constexpr int kTraceStride = 512;        //   0 start, 1 scan end, 2 transition begin, 3 transition end, 4 static part end, 5 SM id
@@ -61,7 +63,8 @@ constexpr int kTraceArrays = 6;
 struct ScanCtl {
     unsigned done;                                      // CTAs that have finished (ticket); the last one resets the set
     unsigned epoch;                                     // launches that have used AND reset this set (release store)
-    unsigned pad[30];
+    unsigned offers;                                    // cascade: phase B offers of the whole grid so far (storm guard)
+    unsigned pad[29];
     unsigned work[kScanWarps * kWorkCounterStride];     // dynamic-tail ticket counters, one 128-byte line each
     u64 gslots[kScanMaxNQ * kCascadeMaxK];              // cascade select: running global top-k, sorted descending
 };
@@ -215,6 +218,7 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
     __shared__ float s_thr[NQ];
     __shared__ int s_count[NQ];
     __shared__ int s_lock[NQ];
+    __shared__ int s_storm;                      // cascade: this CTA has fallen back to its shared-memory lists (see offer_global)
     __shared__ int s_arrived;                    // cascade: warps of this CTA that have left phase A
     __shared__ u64 s_casc[NQ][kCascadeMaxK];     // cascade: the last CTA's copy of the slots
     auto list_of = [&](int q) { return ListRef{&s_thr_key[q], &s_thr[q], &s_count[q], &s_lock[q]}; };
@@ -254,7 +258,10 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         p.trace[kTraceWords + 5 * kTraceStride + blockIdx.x] = smid;
     }
-    if (tid == 0) s_arrived = 0;
+    if (tid == 0) {
+        s_arrived = 0;
+        s_storm = 0;
+    }
     if (tid < NQ) {
         u64 seed = 0ull;
         if (p.seed_keys != nullptr && tid < p.nq_valid) seed = p.seed_keys[p.q_begin + tid];
@@ -304,9 +311,22 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
         }
     };
     // Cascade mode (phase B): straight into the global slots, then pick up the slots' new k-th key.
+    // Guard against an insertion storm (a corpus whose scores RISE along the scan order makes every row beat the
+    // running k-th: each offer is a chain of atomics on the same k words for the whole GPU -- measured 3.0 ms
+    // instead of 0.13 ms on a shard sorted by score): a warp that has made more than kCascadeStormOffers offers,
+    // or that sees the whole grid past kCascadeStormGrid offers (random data needs ~200), switches its CTA back
+    // to the shared-memory lists for the rest of the scan.  The lists are emptied first
+    // (their old content went to the slots at the phase switch, keys in the slots must stay unique) and are
+    // offered to the slots once more when the CTA has finished scanning.
+    int my_offers = 0;
     auto offer_global = [&](long long b, const float (&acc)[NQ][U]) {
+        if (*(volatile int*)&s_storm) {   // uniform
+            offer_list(b, acc);
+            return;
+        }
         const long long myrow = b + 2 * hl + half;
         const bool row_ok = (hl < U) && (myrow < row_end);
+        bool offered = false;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             float s = acc[q][0];
@@ -318,6 +338,7 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
                 const u64 key = make_key(s, (uint32_t)myrow);
                 const bool ins = pass && key > *(volatile u64*)&s_thr_key[q];
                 cascade_insert_warp(slots, p.k, ins, key);
+                offered = offered || __any_sync(kFull, ins);
                 if (p.trace != nullptr) {   // diagnostics: warp-level offers / keys sent to the slots in phase B
                     const unsigned m = __ballot_sync(kFull, ins);
                     if (lane == 0) {
@@ -329,6 +350,23 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
                 adopt_bound(q, __ldcg(slots + p.k - 1));
                 __syncwarp();
             }
+        }
+        unsigned grid_offers = 0u;
+        if (offered) {
+            if (lane == 0) grid_offers = atomicAdd(&p.ctl->offers, 1u);
+            grid_offers = __shfl_sync(kFull, grid_offers, 0);
+        }
+        if (offered && (++my_offers > kCascadeStormOffers || grid_offers >= kCascadeStormGrid) &&
+            !*(volatile int*)&s_storm) {   // uniform
+            for (int q = 0; q < p.nq_valid; ++q) {
+                const ListRef st = list_of(q);
+                spin_acquire(st.lock, lane);
+                *(volatile int*)st.count = 0;        // every lane stores the same value
+                spin_release(st.lock, lane);
+            }
+            __threadfence_block();
+            *(volatile int*)&s_storm = 1;
+            __syncwarp();
         }
     };
 
@@ -542,6 +580,17 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
         }
     }
     __syncthreads();
+    if (cascade && *(volatile int*)&s_storm) {
+        // this CTA fell back to its lists (insertion storm): their content goes to the slots before the ticket
+        if (warp < p.nq_valid) {
+            u64* slots = p.ctl->gslots + warp * kCascadeMaxK;
+            u64* mine = entries + (size_t)warp * p.cap;
+            const int c_mine = list_compact_warp(list_of(warp), mine, p.cap, p.k, lane);
+            __syncwarp();
+            cascade_insert_warp(slots, p.k, lane < c_mine, mine[lane < c_mine ? lane : 0]);
+        }
+        __syncthreads();
+    }
     stamp(1);
     if (!p.early_trigger) grid_dep_launch();   // the next kernel may be scheduled from here on
 
@@ -596,7 +645,10 @@ scan_topk_kernel(const __grid_constant__ ScanParams p) {
             }
         }
     }
-    if (tid == 0) p.ctl->done = 0u;
+    if (tid == 0) {
+        p.ctl->done = 0u;
+        p.ctl->offers = 0u;
+    }
     if (dynamic && tid < kScanWarps) p.ctl->work[tid * kWorkCounterStride] = 0u;
     __threadfence();
     __syncthreads();

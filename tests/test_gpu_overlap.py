@@ -196,3 +196,58 @@ def test_host_completion_flag_and_stream_wait_agree(big):
             idx.search_device(Q[i:i + 1], 10, stable_queries=True)       # something in flight on another stream
         D, I = idx.search(Qh[i:i + 1 + (i % 2)], (10, 3, 16, 50)[i % 4])
         assert np.array_equal(I, want[i][1]) and np.array_equal(D, want[i][0]), i
+
+
+@pytest.mark.parametrize("case", ["duplicates", "ascending", "descending", "all_equal", "two_values", "ascending_large"])
+def test_cascade_select_on_adversarial_data(case):
+    """The cascade select forced onto a 150k-row shard (cascade_min_units = 4) with the inputs that stress it: exact
+    ties (the lower id must win, as in faiss' strict-'>' heap and the oracle), scores that rise with the row index
+    (every row beats the running k-th: an insertion storm into the global slots), scores that fall, all rows equal,
+    and two distinct score values.  Reference: torch fp32 over the bf16 rows the index holds, ties by lower id."""
+    import torch
+    import semantic_search_kd_b200 as pkg
+    dev = torch.device("cuda", 0)
+    n, d = (700_000 if case == "ascending_large" else 150_000), 384   # large: dozens of phase B iterations -> the storm guard
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    X = torch.randn((n, d), generator=g, device=dev)
+    X = X / X.norm(dim=1, keepdim=True)
+    q = torch.randn((2, d), generator=g, device=dev)
+    q = (q / q.norm(dim=1, keepdim=True)).contiguous()
+    if case == "duplicates":
+        X[n // 2:] = X[: n - n // 2]
+    elif case in ("ascending", "descending", "ascending_large"):
+        order = torch.argsort((X.to(torch.bfloat16).float() @ q[0]), descending=(case == "descending"))
+        X = X[order].contiguous()
+    elif case == "all_equal":
+        X[:] = X[0]
+    elif case == "two_values":
+        X[:] = X[0]
+        X[1::3] = X[1]
+    idx = pkg.FlatIPIndex(d, metric="inner_product", device=0)
+    if case != "ascending_large":
+        idx.set_option("cascade_min_units", 4)
+    idx.add(X)
+    Xb = X.to(torch.bfloat16).float()
+    for k in (1, 10, 16):
+        for qq in (q[:1], q):
+            s, ids = idx.search_device(qq, k)
+            torch.cuda.synchronize()
+            sc = qq @ Xb.T                                                  # fp32 reference scores
+            for r in range(qq.shape[0]):
+                got_i, got_s = ids[r].cpu().numpy(), s[r].cpu().numpy()
+                assert len(set(got_i.tolist())) == k and got_i.min() >= 0 and got_i.max() < n
+                assert np.all(np.diff(got_s) <= 0)
+                # our scores: fp32 accumulation of the same products in another order -> compare through a tolerance,
+                # ids through the rule "every returned row scores at least the (k+1)-th best minus the tolerance"
+                ref_sorted, _ = torch.sort(sc[r], descending=True)
+                kth = float(ref_sorted[k - 1])
+                assert np.all(sc[r][torch.from_numpy(got_i).to(dev)].cpu().numpy() >= kth - 2e-5), (case, k, r)
+                assert np.allclose(got_s, ref_sorted[:k].cpu().numpy(), atol=2e-5), (case, k, r)
+                if case in ("all_equal", "duplicates", "two_values"):
+                    # exact ties (identical rows -> identical score bits): the lower id wins, in order
+                    order = torch.argsort(-sc[r], stable=True)[:k]               # stable: equal scores keep id order
+                    assert got_i.tolist() == order.cpu().tolist(), (case, k, r)
+    st = idx.stats()
+    assert st["path"] == 1
+    idx.close()
