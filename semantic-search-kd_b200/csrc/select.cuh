@@ -206,8 +206,10 @@ __device__ __forceinline__ int list_compact_warp(const ListRef& st, u64* entries
     __syncwarp();
     if (c >= k) {   // uniform; every lane stores the same values
         const u64 kth = work[k - 1];
-        *(volatile u64*)st.thr_key = kth;
-        *(volatile float*)st.thr = key_score(kth);
+        if (kth > *(volatile u64*)st.thr_key) {   // never below a bound adopted from outside (scan kernel: the global slots)
+            *(volatile u64*)st.thr_key = kth;
+            *(volatile float*)st.thr = key_score(kth);
+        }
     }
     *(volatile int*)st.count = keep;
     __syncwarp();
