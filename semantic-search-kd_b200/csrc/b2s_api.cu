@@ -1131,6 +1131,8 @@ static int search_host(b2s_index* idx, const float* queries, int64_t nq, int k, 
         flag = reinterpret_cast<volatile unsigned*>(po + ((sbytes + ibytes + 63) & ~(size_t)63));
         idx->host_flag = const_cast<unsigned*>(flag);
         idx->host_seq = ++idx->host_calls;
+        if (idx->host_seq == 0u) idx->host_seq = ++idx->host_calls;   // (wrap-around: 0 means "not yet")
+        *flag = 0u;   // the word moves with (nq, k) and pinned memory is recycled: never trust what it holds
         idx->host_flag_armed = false;
         idx->host_q = queries;                                     // read at launch time, inside this call
         io_ids = reinterpret_cast<int64_t*>(po);                   // pinned host memory is device-accessible (UVA)
