@@ -251,3 +251,23 @@ def test_cascade_select_on_adversarial_data(case):
     st = idx.stats()
     assert st["path"] == 1
     idx.close()
+
+
+def test_completion_word_is_not_trusted_across_handles():
+    """Regression (found by test_ragged_sizes_scan during round 2): the completion word of a host call lives in
+    pinned memory behind the outputs, so it moves with (nq, k), and pinned memory is recycled between handles.  A
+    new handle must never see the value an earlier handle left there and return before its kernel has written."""
+    import semantic_search_kd_b200 as pkg
+    rng = np.random.default_rng(11)
+    for gen in range(6):
+        X = rng.standard_normal((37 + gen, 384)).astype(np.float32)
+        X /= np.linalg.norm(X, axis=1, keepdims=True)
+        q = X[gen:gen + 1] + 0.01 * rng.standard_normal((1, 384)).astype(np.float32)
+        idx = pkg.FlatIPIndex(384, metric="inner_product")
+        idx.set_option("path", 1)
+        idx.add(X)
+        for k in (1, 10, 1, 10):                      # the same call sequence on every handle: same flag values
+            D, I = idx.search(q, k)
+            ref = np.argsort(-(X.astype(np.float64) @ q[0].astype(np.float64)), kind="stable")[:k]
+            assert I[0, 0] == gen and I[0].tolist() == ref.tolist(), (gen, k, I, ref)
+        idx.close()
