@@ -73,3 +73,52 @@ def test_bad_shapes_rejected_before_touching_the_device():
         idx.add(np.zeros((3, 100), np.float32))
     with pytest.raises(pkg.IndexBuildError):
         idx.add(np.zeros((384,), np.float32))
+
+
+def test_small_call_staging_path():
+    """index._small_call (the serving-sized host path: cached staging arrays instead of three ctypes pointers per
+    call) with a fake C entry point: what it passes, what it returns, when it declines."""
+    import ctypes
+    import threading
+    from semantic_search_kd_b200 import index as ix
+
+    class Owner:
+        _h = ctypes.c_void_p(1234)
+
+    calls = []
+
+    def fake(handle, aq, nq, k, as_, ai):
+        q = np.ctypeslib.as_array((ctypes.c_float * (nq * 4)).from_address(aq)).copy()
+        calls.append((handle, q, nq, k))
+        s = np.ctypeslib.as_array((ctypes.c_float * (nq * k)).from_address(as_))
+        i = np.ctypeslib.as_array((ctypes.c_int64 * (nq * k)).from_address(ai))
+        s[:] = np.arange(nq * k, dtype=np.float32)[::-1]
+        i[:] = np.arange(nq * k, dtype=np.int64)
+        return 0
+
+    o = Owner()
+    q = np.arange(8, dtype=np.float32).reshape(2, 4)
+    D, I = ix._small_call(o, fake, "fake", q, 2, 3)
+    assert D.shape == (2, 3) and I.shape == (2, 3) and D.dtype == np.float32 and I.dtype == np.int64
+    assert I.tolist() == [[0, 1, 2], [3, 4, 5]] and D[0, 0] == 5.0
+    assert calls[0][0] is o._h and np.array_equal(calls[0][1], q.reshape(-1)) and calls[0][2:] == (2, 3)
+    D2, I2 = ix._small_call(o, fake, "fake", q + 1, 2, 3)        # results are copies, not views of the staging arrays
+    assert D is not D2 and I.tolist() == [[0, 1, 2], [3, 4, 5]]
+    # too large for the staging arrays -> the caller takes the general path
+    assert ix._small_call(o, fake, "fake", np.zeros((1, ix._SMALL_Q_FLOATS + 1), np.float32), 1, 3) is None
+    assert ix._small_call(o, fake, "fake", q, 2, ix._SMALL_OUT) is None
+    # another thread is inside -> decline instead of sharing the staging arrays
+    lock = o.__dict__["_stage"][0]
+    assert lock.acquire(False)
+    try:
+        out = []
+        t = threading.Thread(target=lambda: out.append(ix._small_call(o, fake, "fake", q, 2, 3)))
+        t.start()
+        t.join()
+        assert out == [None]
+    finally:
+        lock.release()
+    # an error code from the library surfaces as the package's exception and releases the lock
+    with pytest.raises(pkg.DeviceError):
+        ix._small_call(o, lambda *a: pkg._lib.B2S_ERR_CUDA, "fake", q, 2, 3)
+    assert ix._small_call(o, fake, "fake", q, 2, 3) is not None
