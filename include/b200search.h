@@ -140,6 +140,10 @@ B2S_API int b2s_set_id_offset(b2s_index* idx, int64_t offset);
  *   "cascade"     1 (default): k <= 16 on large shards keeps the running global top-k in k sorted
  *                 device slots (lock-free atomicMax insertion) instead of per-CTA lists + merge
  *   "phase_a"     cascade: iterations against the CTA-local lists before the slots take over (0 = auto)
+ *   "phase_a_stagger" cascade: CTA b switches b % this iterations later (default 64, capped by the shard size)
+ *   "transition_mode" cascade A/B switch: 0 (default) CTA-wide phase switch behind a barrier, 1 warp by warp
+ *   "peek_every"  cascade A/B switch: warp 0 re-reads the slots' k-th key every this many iterations (default 0 =
+ *                 only after its own offers)
  *   "trace"       1: the scan kernel stamps %globaltimer at its phase boundaries (b2s_read_trace)
  *   "exchange_timeout_ms" bound of a sharded search's wait for a peer rank (default 10000)
  *   "tc_min_nq"   smallest query batch that takes the tensor path (default 3)
