@@ -10,6 +10,13 @@ against a real file -- SURVEY.md App. C):
            | int32 metric_type (0 = inner product, 1 = L2) | uint64 count (= ntotal*d) | float32[count]
 
 ("IxF2" is the L2 flavour, same body).  Little-endian throughout.
+
+An ``IndexHNSWFlat`` file -- what the reference's ``scripts/build_faiss_index.py`` leaves behind with its default
+``index_type="HNSW"`` -- is ``"IHNf" | the same header | the HNSW graph (five length-prefixed vectors and five
+ints) | the storage index``, and the storage index is a complete flat file ("IxFI" ...) holding every vector.  It is
+the LAST thing in the file, so its position follows from the file size and the outer header alone: the graph
+(whose exact layout differs between faiss versions) is skipped without being parsed, the inner header is
+validated.  An exact index has no use for the graph; the vectors are all it needs.
 """
 from __future__ import annotations
 
@@ -21,6 +28,7 @@ import numpy as np
 
 FOURCC_IP = b"IxFI"
 FOURCC_L2 = b"IxF2"
+FOURCC_HNSW_FLAT = b"IHNf"   # IndexHNSWFlat: what the reference's own build script writes (index_type="HNSW")
 _HEADER = struct.Struct("<4siqqqBi")  # fourcc, d, ntotal, dummy, dummy, is_trained, metric
 HEADER_BYTES = _HEADER.size + 8       # + uint64 count = 45
 
@@ -46,38 +54,57 @@ def write_flat_ip(path: Path, blocks: Iterable[np.ndarray], ntotal: int, dim: in
     return written
 
 
-def read_header(path: Path) -> Tuple[int, int, int]:
-    """(d, ntotal, metric_type) of an IndexFlat file; ValueError for anything else."""
-    with open(Path(path), "rb") as f:
-        head = f.read(_HEADER.size)
-    if len(head) < _HEADER.size:
+def _locate_flat(path: Path) -> Tuple[int, int, int, int]:
+    """(offset of the flat index inside the file, d, ntotal, metric_type) for a flat file or an IndexHNSWFlat file."""
+    path = Path(path)
+    size = path.stat().st_size
+    with open(path, "rb") as f:
+        head = f.read(HEADER_BYTES)
+        if len(head) < _HEADER.size:
+            raise ValueError(f"{path}: truncated FAISS header")
+        fourcc, d, ntotal, _d1, _d2, _trained, metric = _HEADER.unpack(head[:_HEADER.size])
+        if fourcc in (FOURCC_IP, FOURCC_L2):
+            off = 0
+        elif fourcc == FOURCC_HNSW_FLAT:
+            if d <= 0 or ntotal < 0:
+                raise ValueError(f"{path}: implausible header (d={d}, ntotal={ntotal})")
+            off = size - (HEADER_BYTES + ntotal * d * 4)     # the storage index is the tail of the file
+            if off < _HEADER.size:
+                raise ValueError(f"{path}: IndexHNSWFlat file too short for {ntotal} x {d} stored vectors")
+            f.seek(off)
+            inner = f.read(HEADER_BYTES)
+            ifourcc, idim, intotal, _a, _b, _t, imetric = _HEADER.unpack(inner[:_HEADER.size])
+            if ifourcc not in (FOURCC_IP, FOURCC_L2) or idim != d or intotal != ntotal:
+                raise ValueError(f"{path}: no flat storage index ({ntotal} x {d}) at the end of the IndexHNSWFlat file "
+                                 f"(found {ifourcc!r}, {intotal} x {idim}): unsupported faiss version or storage type")
+            metric = imetric
+            head = inner
+        else:
+            raise ValueError(f"{path}: unsupported FAISS index type {fourcc!r}; only flat indexes (IxFI / IxF2) and "
+                             "IndexHNSWFlat (IHNf, whose flat storage is read) can be loaded into the exact-search index")
+    if len(head) < HEADER_BYTES:
         raise ValueError(f"{path}: truncated FAISS header")
-    fourcc, d, ntotal, _d1, _d2, _trained, metric = _HEADER.unpack(head)
-    if fourcc not in (FOURCC_IP, FOURCC_L2):
-        raise ValueError(f"{path}: unsupported FAISS index type {fourcc!r}")
-    return int(d), int(ntotal), int(metric)
+    if metric > 1:
+        raise ValueError(f"{path}: unsupported metric_type {metric}")
+    (count,) = struct.unpack("<Q", head[_HEADER.size:HEADER_BYTES])
+    if count != ntotal * d:
+        raise ValueError(f"{path}: vector count {count} != ntotal*d {ntotal * d}")
+    if size < off + HEADER_BYTES + count * 4:
+        raise ValueError(f"{path}: file shorter than header claims ({size} < {off + HEADER_BYTES + count * 4})")
+    return off, int(d), int(ntotal), int(metric)
+
+
+def read_header(path: Path) -> Tuple[int, int, int]:
+    """(d, ntotal, metric_type) of an IndexFlat / IndexHNSWFlat file; ValueError for anything else."""
+    _off, d, ntotal, metric = _locate_flat(path)
+    return d, ntotal, metric
 
 
 def read_flat(path: Path) -> Tuple[np.ndarray, int]:
-    """Memory-map the vectors of an IndexFlat file.  Returns (fp32 [ntotal, d] memmap, metric)."""
+    """Memory-map the stored vectors of an IndexFlat or IndexHNSWFlat file.  Returns (fp32 [ntotal, d] memmap, metric)."""
     path = Path(path)
-    with open(path, "rb") as f:
-        head = f.read(HEADER_BYTES)
-    if len(head) < HEADER_BYTES:
-        raise ValueError(f"{path}: truncated FAISS header")
-    fourcc, d, ntotal, _d1, _d2, _trained, metric = _HEADER.unpack(head[:_HEADER.size])
-    if fourcc not in (FOURCC_IP, FOURCC_L2):
-        raise ValueError(f"{path}: unsupported FAISS index type {fourcc!r}; only flat indexes "
-                         "(IxFI / IxF2) can be loaded into the exact-search index")
-    if metric > 1:
-        raise ValueError(f"{path}: unsupported metric_type {metric}")
-    (count,) = struct.unpack("<Q", head[_HEADER.size:])
-    if count != ntotal * d:
-        raise ValueError(f"{path}: vector count {count} != ntotal*d {ntotal * d}")
-    expect = HEADER_BYTES + count * 4
-    if path.stat().st_size < expect:
-        raise ValueError(f"{path}: file shorter than header claims ({path.stat().st_size} < {expect})")
+    off, d, ntotal, metric = _locate_flat(path)
     if ntotal == 0:
         return np.zeros((0, d), dtype=np.float32), metric
-    data = np.memmap(path, dtype="<f4", mode="r", offset=HEADER_BYTES, shape=(ntotal, d))
+    data = np.memmap(path, dtype="<f4", mode="r", offset=off + HEADER_BYTES, shape=(ntotal, d))
     return data, metric

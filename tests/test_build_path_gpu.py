@@ -199,3 +199,29 @@ def test_cli_embeddings_build(tmp_path, oracle):
     rep = oracle.compare_topk(D, I, Dr, Ir, X[:4000], Q, tie_tol=TIE_TOL)
     assert rep["ok"] and I[:, 0].tolist() == [5, 3999]
     idx.close()
+
+
+def test_load_reference_hnsw_directory(tmp_path, oracle):
+    """The reference builds `FAISSIndexBuilder(index_type="HNSW")` and saves with faiss.write_index: index.faiss is an
+    IndexHNSWFlat file.  Our load() takes the stored vectors out of it (the graph is of no use to an exact index):
+    a directory written by the reference's own build script is servable as it is."""
+    import sys
+    sys.path.insert(0, str(ROOT / "tests"))
+    from test_host_logic import _write_hnsw_flat
+    import semantic_search_kd_b200 as pkg
+    rng = np.random.default_rng(21)
+    X = rng.standard_normal((2000, 384)).astype(np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    d = tmp_path / "ref_index"
+    d.mkdir()
+    _write_hnsw_flat(d / "index.faiss", X)
+    (d / "doc_ids.json").write_text(json.dumps([f"doc_{i}" for i in range(len(X))]))
+    idx = pkg.FAISSIndexBuilder(embedding_dim=384)            # what /index/load constructs
+    idx.load(d)
+    assert idx.ntotal == 2000 and idx.doc_ids[7] == "doc_7"
+    Q = X[[7, 1999]] + 0.01 * rng.standard_normal((2, 384)).astype(np.float32)
+    D, I = idx.search(Q, 10)
+    Dr, Ir = oracle.flat_ip_topk(X, Q, 10)
+    rep = oracle.compare_topk(D, I, Dr, Ir, X, Q, tie_tol=TIE_TOL)
+    assert rep["ok"] and I[:, 0].tolist() == [7, 1999], rep
+    idx.close()

@@ -95,3 +95,15 @@ def test_load_faiss_written_directory_and_match_faiss(tmp_path, oracle):
         again = faiss.read_index(str(tmp_path / (name + "_resaved") / "index.faiss"))
         assert again.ntotal == len(X)
         ours.close()
+
+
+def test_our_reader_takes_the_vectors_out_of_a_faiss_hnsw_file(tmp_path):
+    """faiss.write_index(IndexHNSWFlat) -- the reference's default index_type -- read by faiss_io.read_flat."""
+    from semantic_search_kd_b200 import faiss_io
+    X = _cases()["dups3000"][0]
+    index = faiss.IndexHNSWFlat(384, 32, faiss.METRIC_INNER_PRODUCT)
+    index.hnsw.efConstruction = 40
+    index.add(X)
+    faiss.write_index(index, str(tmp_path / "index.faiss"))
+    rows, metric = faiss_io.read_flat(tmp_path / "index.faiss")
+    assert metric == 0 and np.array_equal(np.asarray(rows), X)

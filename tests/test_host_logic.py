@@ -26,8 +26,11 @@ def test_faiss_flat_file_layout(tmp_path):
 
 def test_faiss_reader_rejects_other_index_types(tmp_path):
     p = tmp_path / "index.faiss"
-    p.write_bytes(b"IHNf" + b"\0" * 100)
+    p.write_bytes(b"IwPQ" + b"\0" * 100)
     with pytest.raises(ValueError, match="unsupported FAISS index type"):
+        faiss_io.read_flat(p)
+    p.write_bytes(b"IHNf" + b"\0" * 100)             # an HNSW file without a flat storage tail
+    with pytest.raises(ValueError):
         faiss_io.read_flat(p)
     p.write_bytes(b"IxFI" + b"\0" * 10)
     with pytest.raises(ValueError, match="truncated"):
@@ -122,3 +125,44 @@ def test_small_call_staging_path():
     with pytest.raises(pkg.DeviceError):
         ix._small_call(o, lambda *a: pkg._lib.B2S_ERR_CUDA, "fake", q, 2, 3)
     assert ix._small_call(o, fake, "fake", q, 2, 3) is not None
+
+
+def _write_hnsw_flat(path, X, M=32, extra_tail_fields=0):
+    """An IndexHNSWFlat file as faiss 1.7.x lays it out (restated from its index_write.cpp; faiss is absent here):
+    "IHNf" | index header | HNSW {assign_probas f64[], cum_nneighbor_per_level i32[], levels i32[], offsets u64[],
+    neighbors i32[], entry_point, max_level, efConstruction, efSearch, upper_beam (i32 each)} | storage = flat index."""
+    n, d = X.shape
+
+    def vec(fmt, vals):
+        a = np.asarray(vals, dtype=fmt)
+        return struct.pack("<Q", a.size) + a.tobytes()
+
+    levels = np.ones(n, dtype="<i4")
+    offsets = np.arange(n + 1, dtype="<u8") * (2 * M)
+    neighbors = np.full(n * 2 * M, -1, dtype="<i4")
+    body = b"IHNf" + struct.pack("<iqqqBi", d, n, 1 << 20, 1 << 20, 1, 0)
+    body += vec("<f8", [1.0 - 1.0 / M, 0.0]) + vec("<i4", [0, 2 * M, 3 * M]) + vec("<i4", levels) + vec("<u8", offsets)
+    body += vec("<i4", neighbors) + struct.pack("<5i", 0, 0, 200, 64, 1) + b"\0" * (4 * extra_tail_fields)
+    path.write_bytes(body)
+    with open(path, "ab") as f:
+        f.write(b"IxFI" + struct.pack("<iqqqBi", d, n, 1 << 20, 1 << 20, 1, 0) + struct.pack("<Q", n * d))
+        f.write(np.ascontiguousarray(X, dtype="<f4").tobytes())
+
+
+def test_hnsw_flat_file_gives_up_its_vectors(tmp_path):
+    """The reference's own build script writes IndexHNSWFlat (index_type="HNSW"): its directory must load.  The reader
+    takes the flat storage index from the END of the file, so it does not depend on the graph's exact layout
+    (a version with extra HNSW fields reads the same)."""
+    X = unit_rows(123, 384, 7)
+    for extra in (0, 3):
+        p = tmp_path / f"hnsw{extra}.faiss"
+        _write_hnsw_flat(p, X, extra_tail_fields=extra)
+        assert faiss_io.read_header(p) == (384, 123, 0)
+        rows, metric = faiss_io.read_flat(p)
+        assert metric == 0 and rows.shape == (123, 384) and np.array_equal(np.asarray(rows), X)
+    # header says more vectors than the tail holds -> refused, not mis-read
+    raw = bytearray((tmp_path / "hnsw0.faiss").read_bytes())
+    raw[8:16] = struct.pack("<q", 124)
+    (tmp_path / "bad.faiss").write_bytes(bytes(raw))
+    with pytest.raises(ValueError):
+        faiss_io.read_flat(tmp_path / "bad.faiss")
